@@ -1,0 +1,174 @@
+/* svcb.h — C ABI of libsvc_b200.so: the sm_100a SVC inference hot path.
+ *
+ * The reference (PlayVoice/whisper-vits-svc) has no FFI / plugin layer: its hot path sits
+ * behind nn.Module methods.  This header is the boundary a maintainer binds
+ * instead (ctypes stub in INTEGRATION.md); each entry point names the reference code it
+ * replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - activations are fp32, contiguous, [B, C, T] with T innermost unless stated;
+ *   - no allocation, no ownership transfer, no host synchronisation inside a call: the
+ *     caller owns inputs, outputs and the workspace; work is enqueued on `stream`;
+ *   - return 0 on success, <0 = svcb_status; svcb_last_error() gives a thread-local message;
+ *   - a model handle is immutable after creation: concurrent calls on different streams
+ *     are fine when their workspaces differ;
+ *   - sm_100a only, no fallback: svcb_model_create fails with SVCB_E_UNSUPPORTED elsewhere.
+ */
+#ifndef SVCB_H_
+#define SVCB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  SVCB_OK = 0,
+  SVCB_E_BAD_SHAPE = -1,
+  SVCB_E_BAD_ALIGN = -2,
+  SVCB_E_UNSUPPORTED = -3,
+  SVCB_E_CUDA = -4,
+  SVCB_E_MISSING_TENSOR = -5,
+  SVCB_E_WORKSPACE = -6
+} svcb_status;
+
+typedef void* svcb_stream; /* cudaStream_t */
+
+#define SVCB_MAX_UPS 8
+#define SVCB_MAX_RES 4
+
+/* hp.vits.*, hp.gen.*, hp.data.* of configs/base.yaml plus the constants hard-coded at
+ * vits/models.py:220-238 (2 heads, 6 layers, FFN k3, window 4; flow k5, 4 WN layers, 4 flows). */
+typedef struct {
+  int32_t ppg_dim, vec_dim, spk_dim, inter_channels, hidden_channels, filter_channels;
+  int32_t enc_layers, enc_heads, enc_kernel, enc_window;
+  int32_t n_flows, wn_layers, wn_kernel;
+  int32_t gen_input, gen_initial_channel;
+  int32_t n_ups;
+  int32_t up_rates[SVCB_MAX_UPS];
+  int32_t up_kernels[SVCB_MAX_UPS];
+  int32_t n_res;
+  int32_t res_kernels[SVCB_MAX_RES];
+  int32_t res_dilations[SVCB_MAX_RES][3];
+  int32_t sampling_rate;
+  int32_t n_harmonics;   /* 11 = fundamental + 10 overtones (vits_decoder/nsf.py:368) */
+  int32_t precision;     /* 0 = fp32-parity (fp32 FMA / bf16x3 split MMA), 1 = bf16 MMA */
+} svcb_config;
+
+/* One named tensor inside the packed weight blob (host-side table, read at create time). */
+typedef struct {
+  char name[96];
+  uint64_t offset_bytes; /* from the start of the blob, 256-byte aligned */
+  uint64_t numel;        /* fp32 elements */
+} svcb_tensor_entry;
+
+typedef struct svcb_model svcb_model;
+
+/* Optional debugging taps: device pointers (or NULL) that receive a copy of an intermediate.
+ * Index meaning in svcb_tap_id. */
+typedef enum {
+  SVCB_TAP_ENC_FRONT = 0,   /* [B,H,T] after pre+hub+pitch embedding (vits/models.py:47) */
+  SVCB_TAP_ENC_LAYER0 = 1,  /* ..+5: output of encoder layer i (attentions.py:68-70) */
+  SVCB_TAP_ZP = 7,          /* [B,C,T] (models.py:51) */
+  SVCB_TAP_FLOW0 = 8,       /* ..+3: output of coupling layer i (index = flows[2*i]) */
+  SVCB_TAP_GEN_PRE = 12,    /* [B,ch0,T] after conv_pre+Mish (generator.py:178-179) */
+  SVCB_TAP_GEN_UP0 = 13,    /* ..+4: ups[i](x)+noise_convs[i](source) (generator.py:183-186) */
+  SVCB_TAP_GEN_STAGE0 = 18, /* ..+4: mean of the 3 AMP blocks (generator.py:188-194) */
+  SVCB_TAP_COUNT = 24
+} svcb_tap_id;
+
+typedef struct {
+  float* ptr[SVCB_TAP_COUNT];
+} svcb_taps;
+
+const char* svcb_last_error(void);
+int svcb_version(void);
+
+/* Replaces: SynthesizerInfer.__init__ + load_svc_model (svc_inference.py:61-74,163-170).
+ * `dev_blob` holds fp32 tensors already folded/re-laid-out by the host packer
+ * (whisper-vits-svc_b200/pack.py documents every name and layout). The blob must outlive
+ * the handle. */
+int svcb_model_create(const void* dev_blob, size_t blob_bytes,
+                      const svcb_tensor_entry* table_host, int32_t n_entries,
+                      const svcb_config* cfg_host, svcb_model** out);
+void svcb_model_destroy(svcb_model* m);
+
+/* Bytes of caller-owned scratch needed by any of the calls below at (B, T frames). */
+size_t svcb_workspace_bytes(const svcb_model* m, int32_t B, int32_t T);
+
+/* Replaces: Generator.pitch2source (vits_decoder/generator.py:160-165) ->
+ * SourceModuleHnNSF.forward (nsf.py:383-394) -> SineGen (nsf.py:217-316).
+ * f0 [B,T] Hz (0 = unvoiced); rand_ini [B,n_harm] replaces torch.rand (nsf.py:232-235; column 0
+ * is ignored); noise [B, T*hop, n_harm] replaces torch.randn_like (nsf.py:311);
+ * source out [B,1,T*hop]. */
+int svcb_source(const svcb_model* m, const float* f0, const float* rand_ini, const float* noise,
+                float* source, int32_t B, int32_t T, void* ws, size_t ws_bytes, svcb_stream stream);
+
+/* Replaces: Generator.source2wav (generator.py:167-173): x*32768, clamp, int16. */
+int svcb_source2wav(const float* source, int16_t* out, size_t n, svcb_stream stream);
+
+/* Replaces: f0_to_coarse (vits/utils.py:20-33) + TextEncoder.forward (vits/models.py:39-52).
+ * ppg [B,T,ppg_dim] and vec [B,T,vec_dim] are TIME-MAJOR as the reference receives them;
+ * pit [B,T]; lengths [B] int64 (ppg_l); eps [B,C,T] replaces torch.randn_like (models.py:51);
+ * z_p out [B,C,T]. */
+int svcb_prior(const svcb_model* m, const float* ppg, const float* vec, const float* pit,
+               const int64_t* lengths, const float* eps, float* z_p, int32_t B, int32_t T,
+               void* ws, size_t ws_bytes, const svcb_taps* taps, svcb_stream stream);
+
+/* Replaces: ResidualCouplingBlock.forward(reverse=True) (vits/models.py:89-94) incl. Flip and
+ * ResidualCouplingLayer/WN (vits/modules.py:178-203,288-321).  spk [B,spk_dim]; z out [B,C,T]. */
+int svcb_flow(const svcb_model* m, const float* z_p, const int64_t* lengths, const float* spk,
+              float* z, int32_t B, int32_t T, void* ws, size_t ws_bytes, const svcb_taps* taps,
+              svcb_stream stream);
+
+/* Replaces: Generator.inference (vits_decoder/generator.py:175-200).
+ * z [B,gen_input,T] (already multiplied by the mask, as models.py:255 passes it);
+ * source [B,1,T*hop]; wave out [B,1,T*hop]. */
+int svcb_generator(const svcb_model* m, const float* spk, const float* z, const float* source,
+                   float* wave, int32_t B, int32_t T, void* ws, size_t ws_bytes,
+                   const svcb_taps* taps, svcb_stream stream);
+
+/* Replaces: SynthesizerInfer.inference (vits/models.py:251-256) = prior -> flow -> generator. */
+int svcb_infer(const svcb_model* m, const float* ppg, const float* vec, const float* pit,
+               const float* spk, const int64_t* lengths, const float* source, const float* eps,
+               float* wave, int32_t B, int32_t T, void* ws, size_t ws_bytes,
+               const svcb_taps* taps, svcb_stream stream);
+
+/* Number of kernels enqueued by the most recent call on this thread (bench.py's gpu_launches). */
+int64_t svcb_last_launch_count(void);
+
+/* ---- single-operator entry points (unit-test surface; same kernels the pipeline uses) ---- */
+
+/* y[B,Cout,Tout] = act(conv1d(x[B,Cin,Tin], w) + bias); w is the PACKED layout [Cin][K][CoutPad8]
+ * (see pack.py:pack_conv).  Mirrors torch.nn.functional.conv1d as used at every call site
+ * listed in SURVEY.md §8c.  act: 0 none, 1 relu, 2 mish, 3 gelu(erf), 4 tanh. */
+int svcb_op_conv1d(const float* x, const float* w_packed, const float* bias, float* y,
+                   int32_t B, int32_t Cin, int32_t Cout, int32_t Tin, int32_t K, int32_t stride,
+                   int32_t dilation, int32_t pad, int32_t act, svcb_stream stream);
+
+/* Replaces SnakeAlias.forward (vits_decoder/alias/act.py:124-128).  ea = exp(alpha) [C],
+ * inv_b = 1/(exp(beta)+1e-9) [C], fu/fd = the 12 up/down taps. */
+int svcb_op_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,
+                        const float* fu, const float* fd, int32_t B, int32_t C, int32_t L,
+                        svcb_stream stream);
+
+/* y = LayerNorm_C(x + r) * gamma + beta over the channel dim of [B,C,T] (vits/modules.py:19-22;
+ * r may be NULL).  gamma/beta are [C] (gb_batch_stride 0) or [B,C] (stride C: SpeakerAdapter,
+ * vits_decoder/generator.py:36-47). */
+int svcb_op_layernorm_c(const float* x, const float* r, const float* gamma, const float* beta,
+                        float* y, int32_t B, int32_t C, int32_t T, int32_t gb_batch_stride,
+                        float eps, svcb_stream stream);
+
+/* Windowed relative-position self-attention (vits/attentions.py:225-274): qkv [B,3*H,T]
+ * (q | k | v), emb_rel_k / emb_rel_v [2w+1, H/heads], lengths [B] int64, out [B,H,T]. */
+int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
+                          const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
+                          int32_t window, int32_t T, svcb_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVCB_H_ */

@@ -1,0 +1,652 @@
+// C ABI of libsvc_b200.so: model handle, workspace arena and the stage pipelines.
+// Entry points and the reference code each one replaces are documented in include/svcb.h.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace svcb {
+
+static thread_local std::string g_err;
+static thread_local int64_t g_launches = 0;
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch() { ++g_launches; }
+
+struct ConvW {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, cout_pad = 0, k = 1;
+};
+struct SnakeW { const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr; };
+
+struct EncLayer {
+  ConvW qkv, o, ffn1, ffn2;
+  const float *ek, *ev, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+struct FlowLayer {
+  ConvW pre, post;
+  std::vector<ConvW> in, rs;
+  const float *snac_w, *snac_b;
+};
+struct UpStage {
+  std::vector<ConvW> phase;  // one sub-convolution per output phase
+  const float* bias;
+  ConvW noise;
+  int rate, k, pad, taps;
+};
+struct ResBlock {
+  ConvW c1[3], c2[3];
+  SnakeW act[6];
+  int k, dil[3];
+};
+
+}  // namespace svcb
+
+struct svcb_model {
+  svcb_config cfg;
+  int hop = 1;
+  const char* blob = nullptr;
+  size_t blob_bytes = 0;
+  std::map<std::string, std::pair<const float*, uint64_t>> tensors;
+  // resolved views
+  svcb::ConvW pre, hub, proj;
+  const float* pit_emb = nullptr;
+  std::vector<svcb::EncLayer> enc;
+  std::vector<svcb::FlowLayer> flow;
+  const float *ad_sw, *ad_sb, *ad_bw, *ad_bb;
+  svcb::ConvW conv_pre, conv_post;
+  const float *merge_w, *merge_b;
+  std::vector<svcb::UpStage> ups;
+  std::vector<svcb::ResBlock> res;
+  svcb::SnakeW post_act;
+};
+
+namespace svcb {
+
+// ----------------------------------------------------------------------------- arena
+struct Ctx {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  cudaStream_t stream = nullptr;
+  const svcb_taps* taps = nullptr;
+  bool overflow = false;
+
+  template <class T>
+  T* alloc(size_t n) {
+    off = (off + 255) & ~(size_t)255;
+    const size_t o = off;
+    off += n * sizeof(T);
+    if (off > peak) peak = off;
+    if (dry) return reinterpret_cast<T*>((uintptr_t)4096 + o);
+    if (off > cap) { overflow = true; return nullptr; }
+    return reinterpret_cast<T*>(base + o);
+  }
+};
+
+#define RUN(expr)                    \
+  do {                               \
+    if (!ctx.dry) SVCB_TRY(expr);    \
+  } while (0)
+
+static int tap(Ctx& ctx, int id, const float* src, size_t numel) {
+  if (ctx.dry || !ctx.taps || !ctx.taps->ptr[id]) return SVCB_OK;
+  SVCB_CUDA_CHECK(cudaMemcpyAsync(ctx.taps->ptr[id], src, numel * sizeof(float),
+                                  cudaMemcpyDeviceToDevice, ctx.stream));
+  return SVCB_OK;
+}
+
+static int check_ws(Ctx& ctx) {
+  if (ctx.overflow) {
+    set_error("workspace too small: need " + std::to_string(ctx.peak) + " bytes, have " +
+              std::to_string(ctx.cap));
+    return SVCB_E_WORKSPACE;
+  }
+  return SVCB_OK;
+}
+
+// y[B,cout,T] = conv(x[B,cin,T]) with the standard contiguous layouts.
+static ConvParams std_conv(const ConvW& w, const float* x, float* y, int B, int Tin, int Tout,
+                           int pad, int dil = 1, int stride = 1) {
+  ConvParams p;
+  p.x = x; p.sxb = (long long)w.cin * Tin; p.sxc = Tin; p.sxt = 1;
+  p.w = w.w; p.cout_pad = w.cout_pad; p.bias = w.b;
+  p.y = y; p.syb = (long long)w.cout * Tout; p.syc = Tout; p.syt = 1;
+  p.B = B; p.Cin = w.cin; p.Cout = w.cout; p.Tin = Tin;
+  p.K = w.k; p.stride = stride; p.dil = dil; p.pad = pad;
+  p.q0 = 0; p.nq = Tout;
+  return p;
+}
+
+__global__ void mask_mul_kernel(float* __restrict__ x, const long long* __restrict__ lengths, int C,
+                                int T) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
+  if (t < T && t >= lengths[b]) x[((long long)b * C + c) * T + t] = 0.f;
+}
+static int launch_mask_mul(float* x, const long long* lengths, int B, int C, int T, cudaStream_t s) {
+  dim3 grid((T + 127) / 128, C, B);
+  mask_mul_kernel<<<grid, 128, 0, s>>>(x, lengths, C, T);
+  SVCB_LAUNCH_CHECK("mask_mul");
+  return SVCB_OK;
+}
+
+// ----------------------------------------------------------------------------- prior encoder
+static int run_prior(const svcb_model* m, Ctx& ctx, const float* ppg, const float* vec,
+                     const float* pit, const long long* lengths, const float* eps, float* z_p, int B,
+                     int T) {
+  const svcb_config& c = m->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, Fc = c.filter_channels;
+  cudaStream_t s = ctx.stream;
+  float* x = ctx.alloc<float>((size_t)B * H * T);
+  float* y = ctx.alloc<float>((size_t)B * H * T);
+  float* qkv = ctx.alloc<float>((size_t)B * 3 * H * T);
+  float* att = ctx.alloc<float>((size_t)B * H * T);
+  float* hbuf = ctx.alloc<float>((size_t)B * Fc * T);
+  float* stats = ctx.alloc<float>((size_t)B * 2 * C * T);
+  SVCB_TRY(check_ws(ctx));
+  {  // pre / hub on time-major inputs (vits/models.py:40-46)
+    ConvParams p = std_conv(m->pre, ppg, x, B, T, T, 2);
+    p.sxb = (long long)T * c.ppg_dim; p.sxc = 1; p.sxt = c.ppg_dim;
+    p.lengths = lengths; p.flags = CONV_OUT_MASK;
+    RUN(launch_conv1d(p, s));
+    ConvParams q = std_conv(m->hub, vec, x, B, T, T, 2);
+    q.sxb = (long long)T * c.vec_dim; q.sxc = 1; q.sxt = c.vec_dim;
+    q.lengths = lengths; q.flags = CONV_OUT_MASK; q.res = x;
+    RUN(launch_conv1d(q, s));
+  }
+  RUN(launch_pitch_embed_add(x, pit, m->pit_emb, B, H, T, s));
+  SVCB_TRY(tap(ctx, SVCB_TAP_ENC_FRONT, x, (size_t)B * H * T));
+  RUN(launch_mask_mul(x, lengths, B, H, T, s));  // Encoder.forward: x = x * x_mask
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const EncLayer& L = m->enc[i];
+    RUN(launch_conv1d(std_conv(L.qkv, x, qkv, B, T, T, 0), s));
+    RUN(launch_rel_attention(qkv, L.ek, L.ev, lengths, att, B, H, c.enc_heads, c.enc_window, T, s));
+    RUN(launch_conv1d(std_conv(L.o, att, y, B, T, T, 0), s));
+    RUN(launch_layernorm_c(x, y, L.ln1g, L.ln1b, x, B, H, T, 0, 1e-5f, s));
+    const int pl = (c.enc_kernel - 1) / 2;
+    ConvParams f1 = std_conv(L.ffn1, x, hbuf, B, T, T, pl);
+    f1.lengths = lengths; f1.flags = CONV_IN_MASK; f1.act = ACT_RELU;
+    RUN(launch_conv1d(f1, s));
+    ConvParams f2 = std_conv(L.ffn2, hbuf, y, B, T, T, pl);
+    f2.lengths = lengths; f2.flags = CONV_IN_MASK | CONV_OUT_MASK;
+    RUN(launch_conv1d(f2, s));
+    RUN(launch_layernorm_c(x, y, L.ln2g, L.ln2b, x, B, H, T, 0, 1e-5f, s));
+    if (i < 6) SVCB_TRY(tap(ctx, SVCB_TAP_ENC_LAYER0 + i, x, (size_t)B * H * T));
+  }
+  ConvParams pj = std_conv(m->proj, x, stats, B, T, T, 0);
+  pj.lengths = lengths; pj.flags = CONV_IN_MASK | CONV_OUT_MASK;
+  RUN(launch_conv1d(pj, s));
+  RUN(launch_reparam(stats, eps, lengths, z_p, B, C, T, s));
+  SVCB_TRY(tap(ctx, SVCB_TAP_ZP, z_p, (size_t)B * C * T));
+  return SVCB_OK;
+}
+
+// ----------------------------------------------------------------------------- flow (reverse)
+static int run_flow(const svcb_model* m, Ctx& ctx, const float* z_p, const long long* lengths,
+                    const float* spk, float* z, int B, int T) {
+  const svcb_config& c = m->cfg;
+  const int H = c.hidden_channels, C = c.inter_channels, half = C / 2;
+  cudaStream_t s = ctx.stream;
+  float* ya = ctx.alloc<float>((size_t)B * C * T);
+  float* yb = ctx.alloc<float>((size_t)B * C * T);
+  float* sp = ctx.alloc<float>((size_t)B * C);
+  float* x0n = ctx.alloc<float>((size_t)B * half * T);
+  float* h = ctx.alloc<float>((size_t)B * H * T);
+  float* g = ctx.alloc<float>((size_t)B * H * T);
+  float* rs = ctx.alloc<float>((size_t)B * 2 * H * T);
+  float* out = ctx.alloc<float>((size_t)B * H * T);
+  float* mm = ctx.alloc<float>((size_t)B * half * T);
+  SVCB_TRY(check_ws(ctx));
+  const float* cur = z_p;
+  for (int f = c.n_flows - 1; f >= 0; --f) {
+    const FlowLayer& F = m->flow[f];
+    float* Y = (f == 0) ? z : (((c.n_flows - 1 - f) & 1) ? yb : ya);
+    RUN(launch_linear_small(spk, F.snac_w, F.snac_b, sp, B, c.spk_dim, C, s));
+    RUN(launch_coupling_pre(cur, sp, lengths, Y, x0n, B, C, T, s));
+    ConvParams pp = std_conv(F.pre, x0n, h, B, T, T, 0);
+    pp.lengths = lengths; pp.flags = CONV_OUT_MASK;
+    RUN(launch_conv1d(pp, s));
+    const int nl = c.wn_layers;
+    for (int l = 0; l < nl; ++l) {
+      ConvParams pi = std_conv(F.in[l], h, g, B, T, T, (c.wn_kernel - 1) / 2);
+      pi.flags = CONV_GATE;
+      pi.syb = (long long)H * T;  // gated output has H channels
+      RUN(launch_conv1d(pi, s));
+      RUN(launch_conv1d(std_conv(F.rs[l], g, rs, B, T, T, 0), s));
+      RUN(launch_wn_update(h, out, rs, lengths, B, H, T, l == 0, l == nl - 1, s));
+    }
+    ConvParams po = std_conv(F.post, out, mm, B, T, T, 0);
+    po.lengths = lengths; po.flags = CONV_OUT_MASK;
+    RUN(launch_conv1d(po, s));
+    RUN(launch_coupling_post(cur, sp, mm, lengths, Y, B, C, T, s));
+    if (f < 4) SVCB_TRY(tap(ctx, SVCB_TAP_FLOW0 + f, Y, (size_t)B * C * T));
+    cur = Y;
+  }
+  return SVCB_OK;
+}
+
+// ----------------------------------------------------------------------------- generator
+static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* X, float* ACC,
+                         float* T1, float* T2, float* RA, float* RB, int B, int ch, int L) {
+  cudaStream_t s = ctx.stream;
+  const int nres = m->cfg.n_res;
+  for (int j = 0; j < nres; ++j) {
+    const ResBlock& R = m->res[stage * nres + j];
+    const float* cur = X;
+    for (int d = 0; d < 3; ++d) {
+      const SnakeW& a1 = R.act[2 * d];
+      const SnakeW& a2 = R.act[2 * d + 1];
+      RUN(launch_snake_alias(cur, T1, a1.ea, a1.ib, a1.fu, a1.fd, B, ch, L, s));
+      RUN(launch_conv1d(std_conv(R.c1[d], T1, T2, B, L, L, R.dil[d] * (R.k - 1) / 2, R.dil[d]), s));
+      RUN(launch_snake_alias(T2, T1, a2.ea, a2.ib, a2.fu, a2.fd, B, ch, L, s));
+      ConvParams p = std_conv(R.c2[d], T1, nullptr, B, L, L, (R.k - 1) / 2);
+      p.res = cur;
+      if (d < 2) {
+        p.y = (d == 0) ? RA : RB;
+      } else {  // last unit of the block: fold into the stage mean (generator.py:188-194)
+        p.y = ACC;
+        if (j > 0) p.flags |= CONV_ACCUM;
+        if (j == nres - 1) p.out_div = (float)nres;
+      }
+      RUN(launch_conv1d(p, s));
+      cur = p.y;
+    }
+  }
+  return SVCB_OK;
+}
+
+static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const float* z,
+                         const float* source, float* wave, int B, int T) {
+  const svcb_config& c = m->cfg;
+  cudaStream_t s = ctx.stream;
+  const int U = c.gen_input;
+  const long long Ltot = (long long)T * m->hop;
+  float* sc = ctx.alloc<float>((size_t)B * U);
+  float* bi = ctx.alloc<float>((size_t)B * U);
+  float* xa = ctx.alloc<float>((size_t)B * U * T);
+  float* x0 = ctx.alloc<float>((size_t)B * c.gen_initial_channel * T);
+  // temporaries sized for the largest stage
+  size_t max_stage = 0;
+  {
+    int ch = c.gen_initial_channel; long long L = T;
+    for (int i = 0; i < c.n_ups; ++i) { ch /= 2; L *= c.up_rates[i]; max_stage = std::max<size_t>(max_stage, (size_t)B * ch * L); }
+  }
+  float* T1 = ctx.alloc<float>(max_stage);
+  float* T2 = ctx.alloc<float>(max_stage);
+  float* RA = ctx.alloc<float>(max_stage);
+  float* RB = ctx.alloc<float>(max_stage);
+  SVCB_TRY(check_ws(ctx));
+
+  RUN(launch_linear_small(spk, m->ad_sw, m->ad_sb, sc, B, c.spk_dim, U, s));
+  RUN(launch_linear_small(spk, m->ad_bw, m->ad_bb, bi, B, c.spk_dim, U, s));
+  RUN(launch_layernorm_c(z, nullptr, sc, bi, xa, B, U, T, U, 1e-5f, s));
+  {
+    ConvParams p = std_conv(m->conv_pre, xa, x0, B, T, T, 3);
+    p.act = ACT_MISH;
+    RUN(launch_conv1d(p, s));
+  }
+  SVCB_TRY(tap(ctx, SVCB_TAP_GEN_PRE, x0, (size_t)B * c.gen_initial_channel * T));
+
+  const float* x = x0;
+  int ch = c.gen_initial_channel;
+  int L = T;
+  for (int i = 0; i < c.n_ups; ++i) {
+    const UpStage& us = m->ups[i];
+    const int chn = ch / 2, Ln = L * us.rate;
+    float* X = ctx.alloc<float>((size_t)B * chn * Ln);
+    float* ACC = ctx.alloc<float>((size_t)B * chn * Ln);
+    SVCB_TRY(check_ws(ctx));
+    // ConvTranspose1d as `rate` polyphase sub-convolutions (generator.py:183)
+    for (int r = 0; r < us.rate; ++r) {
+      ConvParams p = std_conv(us.phase[r], x, X, B, L, Ln, us.taps - 1);
+      p.bias = us.bias;
+      const int pr = us.pad - r;
+      p.q0 = pr > 0 ? (pr + us.rate - 1) / us.rate : 0;
+      const int qmax = (Ln - 1 + us.pad - r) / us.rate;
+      p.nq = qmax - p.q0 + 1;
+      p.out_mul = us.rate; p.out_off = r - us.pad;
+      RUN(launch_conv1d(p, s));
+    }
+    {  // noise_convs[i](har_source) added in place (generator.py:185-186)
+      int sf = 1;
+      for (int k2 = i + 1; k2 < c.n_ups; ++k2) sf *= c.up_rates[k2];
+      const bool last = (i + 1 == c.n_ups);
+      ConvParams p;
+      p.x = source; p.sxb = Ltot; p.sxc = Ltot; p.sxt = 1;
+      p.w = us.noise.w; p.cout_pad = us.noise.cout_pad; p.bias = us.noise.b;
+      p.y = X; p.syb = (long long)chn * Ln; p.syc = Ln; p.syt = 1;
+      p.B = B; p.Cin = 1; p.Cout = chn; p.Tin = (int)Ltot;
+      p.K = us.noise.k; p.stride = last ? 1 : sf; p.dil = 1; p.pad = last ? 0 : sf / 2;
+      p.q0 = 0; p.nq = Ln; p.flags = CONV_ACCUM;
+      RUN(launch_conv1d(p, s));
+    }
+    SVCB_TRY(tap(ctx, SVCB_TAP_GEN_UP0 + i, X, (size_t)B * chn * Ln));
+    SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, B, chn, Ln));
+    SVCB_TRY(tap(ctx, SVCB_TAP_GEN_STAGE0 + i, ACC, (size_t)B * chn * Ln));
+    x = ACC; ch = chn; L = Ln;
+  }
+  // activation_post + conv_post + tanh (generator.py:196-199)
+  RUN(launch_snake_alias(x, T1, m->post_act.ea, m->post_act.ib, m->post_act.fu, m->post_act.fd, B, ch, L, s));
+  {
+    ConvParams p = std_conv(m->conv_post, T1, wave, B, L, L, 3);
+    p.act = ACT_TANH;
+    RUN(launch_conv1d(p, s));
+  }
+  return SVCB_OK;
+}
+
+// ----------------------------------------------------------------------------- model creation
+struct Resolver {
+  const svcb_model* m;
+  bool ok = true;
+  std::string missing;
+  const float* get(const std::string& name, uint64_t min_numel = 0) {
+    auto it = m->tensors.find(name);
+    if (it == m->tensors.end() || it->second.second < min_numel) {
+      if (ok) missing = name;
+      ok = false;
+      return nullptr;
+    }
+    return it->second.first;
+  }
+  ConvW conv(const std::string& prefix, int cin, int cout, int k, bool bias = true) {
+    ConvW w;
+    w.cin = cin; w.cout = cout; w.k = k; w.cout_pad = (cout + 7) / 8 * 8;
+    w.w = get(prefix + ".w", (uint64_t)cin * k * w.cout_pad);
+    w.b = bias ? get(prefix + ".b", cout) : nullptr;
+    return w;
+  }
+  SnakeW snake(const std::string& prefix, int ch) {
+    SnakeW s;
+    s.ea = get(prefix + ".ea", ch); s.ib = get(prefix + ".ib", ch);
+    s.fu = get(prefix + ".fu", 12); s.fd = get(prefix + ".fd", 12);
+    return s;
+  }
+};
+
+static int resolve(svcb_model* m) {
+  const svcb_config& c = m->cfg;
+  Resolver R{m};
+  const int H = c.hidden_channels, C = c.inter_channels;
+  m->pre = R.conv("enc_p.pre", c.ppg_dim, H, 5);
+  m->hub = R.conv("enc_p.hub", c.vec_dim, H, 5);
+  m->pit_emb = R.get("enc_p.pit", 256ull * H);
+  m->enc.resize(c.enc_layers);
+  for (int i = 0; i < c.enc_layers; ++i) {
+    const std::string p = "enc." + std::to_string(i);
+    EncLayer& L = m->enc[i];
+    L.qkv = R.conv(p + ".qkv", H, 3 * H, 1);
+    L.o = R.conv(p + ".o", H, H, 1);
+    L.ffn1 = R.conv(p + ".ffn1", H, c.filter_channels, c.enc_kernel);
+    L.ffn2 = R.conv(p + ".ffn2", c.filter_channels, H, c.enc_kernel);
+    const uint64_t nr = (uint64_t)(2 * c.enc_window + 1) * (H / c.enc_heads);
+    L.ek = R.get(p + ".ek", nr); L.ev = R.get(p + ".ev", nr);
+    L.ln1g = R.get(p + ".ln1.g", H); L.ln1b = R.get(p + ".ln1.b", H);
+    L.ln2g = R.get(p + ".ln2.g", H); L.ln2b = R.get(p + ".ln2.b", H);
+  }
+  m->proj = R.conv("enc_p.proj", H, 2 * C, 1);
+  m->flow.resize(c.n_flows);
+  for (int f = 0; f < c.n_flows; ++f) {
+    const std::string p = "flow." + std::to_string(f);
+    FlowLayer& F = m->flow[f];
+    F.pre = R.conv(p + ".pre", C / 2, H, 1);
+    F.post = R.conv(p + ".post", H, C / 2, 1);
+    F.snac_w = R.get(p + ".snac.w", (uint64_t)C * c.spk_dim);
+    F.snac_b = R.get(p + ".snac.b", C);
+    for (int l = 0; l < c.wn_layers; ++l) {
+      F.in.push_back(R.conv(p + ".in." + std::to_string(l), H, 2 * H, c.wn_kernel));
+      F.rs.push_back(R.conv(p + ".rs." + std::to_string(l), H, l + 1 < c.wn_layers ? 2 * H : H, 1));
+    }
+  }
+  const int U = c.gen_input;
+  m->ad_sw = R.get("dec.adapter.scale.w", (uint64_t)U * c.spk_dim);
+  m->ad_sb = R.get("dec.adapter.scale.b", U);
+  m->ad_bw = R.get("dec.adapter.bias.w", (uint64_t)U * c.spk_dim);
+  m->ad_bb = R.get("dec.adapter.bias.b", U);
+  m->conv_pre = R.conv("dec.conv_pre", U, c.gen_initial_channel, 7);
+  m->merge_w = R.get("dec.merge_w", c.n_harmonics);
+  m->merge_b = R.get("dec.merge_b", 1);
+  m->ups.resize(c.n_ups);
+  m->hop = 1;
+  int ch = c.gen_initial_channel;
+  for (int i = 0; i < c.n_ups; ++i) {
+    UpStage& us = m->ups[i];
+    us.rate = c.up_rates[i]; us.k = c.up_kernels[i];
+    us.pad = (us.k - us.rate) / 2;
+    us.taps = (us.k + us.rate - 1) / us.rate;
+    m->hop *= us.rate;
+    const std::string p = "dec.ups." + std::to_string(i);
+    for (int r = 0; r < us.rate; ++r)
+      us.phase.push_back(R.conv(p + ".ph" + std::to_string(r), ch, ch / 2, us.taps, false));
+    us.bias = R.get(p + ".b", ch / 2);
+    ch /= 2;
+  }
+  ch = c.gen_initial_channel;
+  for (int i = 0; i < c.n_ups; ++i) {
+    int sf = 1;
+    for (int k2 = i + 1; k2 < c.n_ups; ++k2) sf *= c.up_rates[k2];
+    const int nk = (i + 1 == c.n_ups) ? 1 : 2 * sf;
+    m->ups[i].noise = R.conv("dec.noise." + std::to_string(i), 1, ch / 2, nk);
+    ch /= 2;
+  }
+  m->res.resize((size_t)c.n_ups * c.n_res);
+  ch = c.gen_initial_channel;
+  for (int i = 0; i < c.n_ups; ++i) {
+    ch /= 2;
+    for (int j = 0; j < c.n_res; ++j) {
+      ResBlock& rb = m->res[(size_t)i * c.n_res + j];
+      rb.k = c.res_kernels[j];
+      const std::string p = "dec.res." + std::to_string(i * c.n_res + j);
+      for (int d = 0; d < 3; ++d) {
+        rb.dil[d] = c.res_dilations[j][d];
+        rb.c1[d] = R.conv(p + ".c1." + std::to_string(d), ch, ch, rb.k);
+        rb.c2[d] = R.conv(p + ".c2." + std::to_string(d), ch, ch, rb.k);
+      }
+      for (int a = 0; a < 6; ++a) rb.act[a] = R.snake(p + ".act." + std::to_string(a), ch);
+    }
+  }
+  m->post_act = R.snake("dec.post.act", ch);
+  m->conv_post = R.conv("dec.conv_post", ch, 1, 7, false);
+  if (!R.ok) {
+    set_error("tensor missing or too small in packed blob: " + R.missing);
+    return SVCB_E_MISSING_TENSOR;
+  }
+  return SVCB_OK;
+}
+
+static int validate_cfg(const svcb_config& c) {
+  if (c.n_ups < 1 || c.n_ups > SVCB_MAX_UPS || c.n_res < 1 || c.n_res > SVCB_MAX_RES) {
+    set_error("config: n_ups / n_res out of range");
+    return SVCB_E_BAD_SHAPE;
+  }
+  if (c.inter_channels % 2 || c.hidden_channels % c.enc_heads || c.hidden_channels / c.enc_heads != 96) {
+    set_error("config: hidden_channels/heads must be 96 and inter_channels even");
+    return SVCB_E_UNSUPPORTED;
+  }
+  if (c.n_harmonics < 1 || c.n_harmonics > 32) { set_error("config: n_harmonics"); return SVCB_E_BAD_SHAPE; }
+  if (c.gen_initial_channel % (1 << c.n_ups)) {
+    set_error("config: gen_initial_channel must be divisible by 2^n_ups");
+    return SVCB_E_BAD_SHAPE;
+  }
+  return SVCB_OK;
+}
+
+}  // namespace svcb
+
+using namespace svcb;
+
+extern "C" {
+
+const char* svcb_last_error(void) { return g_err.c_str(); }
+int svcb_version(void) { return 100; }
+int64_t svcb_last_launch_count(void) { return g_launches; }
+
+int svcb_model_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host,
+                      int32_t n_entries, const svcb_config* cfg_host, svcb_model** out) {
+  if (!dev_blob || !table_host || !cfg_host || !out) { set_error("null argument"); return SVCB_E_BAD_SHAPE; }
+  if (((uintptr_t)dev_blob & 255) != 0) { set_error("weight blob must be 256-byte aligned"); return SVCB_E_BAD_ALIGN; }
+  int dev = 0;
+  SVCB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SVCB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) {
+    set_error("libsvc_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major) +
+              std::to_string(prop.minor));
+    return SVCB_E_UNSUPPORTED;
+  }
+  SVCB_TRY(validate_cfg(*cfg_host));
+  svcb_model* m = new svcb_model();
+  m->cfg = *cfg_host;
+  m->blob = static_cast<const char*>(dev_blob);
+  m->blob_bytes = blob_bytes;
+  for (int i = 0; i < n_entries; ++i) {
+    const svcb_tensor_entry& e = table_host[i];
+    if (e.offset_bytes % 256 != 0 || e.offset_bytes + e.numel * sizeof(float) > blob_bytes) {
+      set_error(std::string("bad table entry: ") + e.name);
+      delete m;
+      return SVCB_E_BAD_ALIGN;
+    }
+    std::string nm(e.name, strnlen(e.name, sizeof(e.name)));
+    m->tensors[nm] = {reinterpret_cast<const float*>(m->blob + e.offset_bytes), e.numel};
+  }
+  const int st = resolve(m);
+  if (st != SVCB_OK) { delete m; return st; }
+  *out = m;
+  return SVCB_OK;
+}
+
+void svcb_model_destroy(svcb_model* m) { delete m; }
+
+size_t svcb_workspace_bytes(const svcb_model* m, int32_t B, int32_t T) {
+  if (!m || B <= 0 || T <= 0) return 0;
+  size_t peak = 0;
+  {
+    Ctx ctx; ctx.dry = true;
+    float* zp = ctx.alloc<float>((size_t)B * m->cfg.inter_channels * T);
+    float* z = ctx.alloc<float>((size_t)B * m->cfg.inter_channels * T);
+    const size_t mark = ctx.off;
+    run_prior(m, ctx, nullptr, nullptr, nullptr, nullptr, nullptr, zp, B, T);
+    ctx.off = mark;
+    run_flow(m, ctx, zp, nullptr, nullptr, z, B, T);
+    ctx.off = mark;
+    run_generator(m, ctx, nullptr, z, nullptr, nullptr, B, T);
+    peak = ctx.peak;
+  }
+  peak = std::max(peak, source_scan_ws_bytes(B, T, m->cfg.n_harmonics) + 256);
+  return peak + 4096;
+}
+
+static int make_ctx(Ctx& ctx, void* ws, size_t ws_bytes, const svcb_taps* taps, svcb_stream stream) {
+  if (!ws || ((uintptr_t)ws & 255)) { set_error("workspace must be non-null and 256-byte aligned"); return SVCB_E_BAD_ALIGN; }
+  ctx.base = static_cast<char*>(ws); ctx.cap = ws_bytes; ctx.taps = taps;
+  ctx.stream = static_cast<cudaStream_t>(stream);
+  return SVCB_OK;
+}
+
+int svcb_source(const svcb_model* m, const float* f0, const float* rand_ini, const float* noise,
+                float* source, int32_t B, int32_t T, void* ws, size_t ws_bytes, svcb_stream stream) {
+  g_launches = 0;
+  if (!m || B <= 0 || T <= 0) { set_error("svcb_source: bad shape"); return SVCB_E_BAD_SHAPE; }
+  Ctx ctx;
+  SVCB_TRY(make_ctx(ctx, ws, ws_bytes, nullptr, stream));
+  double* scan = ctx.alloc<double>(source_scan_ws_bytes(B, T, m->cfg.n_harmonics) / sizeof(double));
+  SVCB_TRY(check_ws(ctx));
+  return launch_source(f0, rand_ini, noise, m->merge_w, m->merge_b, source, scan, B, T, m->hop,
+                       m->cfg.n_harmonics, (float)m->cfg.sampling_rate, ctx.stream);
+}
+
+int svcb_source2wav(const float* source, int16_t* out, size_t n, svcb_stream stream) {
+  g_launches = 0;
+  return launch_source2wav(source, out, n, static_cast<cudaStream_t>(stream));
+}
+
+int svcb_prior(const svcb_model* m, const float* ppg, const float* vec, const float* pit,
+               const int64_t* lengths, const float* eps, float* z_p, int32_t B, int32_t T, void* ws,
+               size_t ws_bytes, const svcb_taps* taps, svcb_stream stream) {
+  g_launches = 0;
+  if (!m || B <= 0 || T <= 0 || !lengths) { set_error("svcb_prior: bad shape or null lengths"); return SVCB_E_BAD_SHAPE; }
+  Ctx ctx;
+  SVCB_TRY(make_ctx(ctx, ws, ws_bytes, taps, stream));
+  return run_prior(m, ctx, ppg, vec, pit, reinterpret_cast<const long long*>(lengths), eps, z_p, B, T);
+}
+
+int svcb_flow(const svcb_model* m, const float* z_p, const int64_t* lengths, const float* spk,
+              float* z, int32_t B, int32_t T, void* ws, size_t ws_bytes, const svcb_taps* taps,
+              svcb_stream stream) {
+  g_launches = 0;
+  if (!m || B <= 0 || T <= 0 || !lengths) { set_error("svcb_flow: bad shape or null lengths"); return SVCB_E_BAD_SHAPE; }
+  Ctx ctx;
+  SVCB_TRY(make_ctx(ctx, ws, ws_bytes, taps, stream));
+  return run_flow(m, ctx, z_p, reinterpret_cast<const long long*>(lengths), spk, z, B, T);
+}
+
+int svcb_generator(const svcb_model* m, const float* spk, const float* z, const float* source,
+                   float* wave, int32_t B, int32_t T, void* ws, size_t ws_bytes,
+                   const svcb_taps* taps, svcb_stream stream) {
+  g_launches = 0;
+  if (!m || B <= 0 || T <= 0) { set_error("svcb_generator: bad shape"); return SVCB_E_BAD_SHAPE; }
+  Ctx ctx;
+  SVCB_TRY(make_ctx(ctx, ws, ws_bytes, taps, stream));
+  return run_generator(m, ctx, spk, z, source, wave, B, T);
+}
+
+int svcb_infer(const svcb_model* m, const float* ppg, const float* vec, const float* pit,
+               const float* spk, const int64_t* lengths, const float* source, const float* eps,
+               float* wave, int32_t B, int32_t T, void* ws, size_t ws_bytes, const svcb_taps* taps,
+               svcb_stream stream) {
+  g_launches = 0;
+  if (!m || B <= 0 || T <= 0 || !lengths) { set_error("svcb_infer: bad shape or null lengths"); return SVCB_E_BAD_SHAPE; }
+  Ctx ctx;
+  SVCB_TRY(make_ctx(ctx, ws, ws_bytes, taps, stream));
+  const long long* len = reinterpret_cast<const long long*>(lengths);
+  float* zp = ctx.alloc<float>((size_t)B * m->cfg.inter_channels * T);
+  float* z = ctx.alloc<float>((size_t)B * m->cfg.inter_channels * T);
+  SVCB_TRY(check_ws(ctx));
+  const size_t mark = ctx.off;
+  SVCB_TRY(run_prior(m, ctx, ppg, vec, pit, len, eps, zp, B, T));
+  ctx.off = mark;
+  SVCB_TRY(run_flow(m, ctx, zp, len, spk, z, B, T));
+  ctx.off = mark;
+  return run_generator(m, ctx, spk, z, source, wave, B, T);
+}
+
+// ---- single-operator entry points
+int svcb_op_conv1d(const float* x, const float* w_packed, const float* bias, float* y, int32_t B,
+                   int32_t Cin, int32_t Cout, int32_t Tin, int32_t K, int32_t stride,
+                   int32_t dilation, int32_t pad, int32_t act, svcb_stream stream) {
+  g_launches = 0;
+  const int Tout = (Tin + 2 * pad - dilation * (K - 1) - 1) / stride + 1;
+  if (Tout <= 0) { set_error("conv1d: empty output"); return SVCB_E_BAD_SHAPE; }
+  ConvW w; w.w = w_packed; w.b = bias; w.cin = Cin; w.cout = Cout; w.cout_pad = (Cout + 7) / 8 * 8; w.k = K;
+  ConvParams p = std_conv(w, x, y, B, Tin, Tout, pad, dilation, stride);
+  p.act = act;
+  return launch_conv1d(p, static_cast<cudaStream_t>(stream));
+}
+
+int svcb_op_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,
+                        const float* fu, const float* fd, int32_t B, int32_t C, int32_t L,
+                        svcb_stream stream) {
+  g_launches = 0;
+  return launch_snake_alias(x, y, ea, inv_b, fu, fd, B, C, L, static_cast<cudaStream_t>(stream));
+}
+
+int svcb_op_layernorm_c(const float* x, const float* r, const float* gamma, const float* beta,
+                        float* y, int32_t B, int32_t C, int32_t T, int32_t gb_batch_stride,
+                        float eps, svcb_stream stream) {
+  g_launches = 0;
+  return launch_layernorm_c(x, r, gamma, beta, y, B, C, T, gb_batch_stride, eps,
+                            static_cast<cudaStream_t>(stream));
+}
+
+int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
+                          const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
+                          int32_t window, int32_t T, svcb_stream stream) {
+  g_launches = 0;
+  return launch_rel_attention(qkv, emb_rel_k, emb_rel_v, reinterpret_cast<const long long*>(lengths),
+                              out, B, H, heads, window, T, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,109 @@
+// Shared declarations for libsvc_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "svcb.h"
+
+namespace svcb {
+
+void set_error(const std::string& msg);
+void count_launch();
+
+#define SVCB_CUDA_CHECK(expr)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      ::svcb::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+      return SVCB_E_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define SVCB_LAUNCH_CHECK(what)                                                          \
+  do {                                                                                   \
+    ::svcb::count_launch();                                                              \
+    cudaError_t _e = cudaGetLastError();                                                 \
+    if (_e != cudaSuccess) {                                                             \
+      ::svcb::set_error(std::string("launch ") + what + ": " + cudaGetErrorString(_e));  \
+      return SVCB_E_CUDA;                                                                \
+    }                                                                                    \
+  } while (0)
+
+#define SVCB_TRY(expr)            \
+  do {                            \
+    int _s = (expr);              \
+    if (_s != SVCB_OK) return _s; \
+  } while (0)
+
+// ----------------------------------------------------------------------------- conv1d
+enum ConvFlags : int {
+  CONV_IN_MASK = 1,    // x[b,:,t] treated as 0 for t >= lengths[b]
+  CONV_OUT_MASK = 2,   // result multiplied by (t_out < lengths[b])
+  CONV_GATE = 4,       // packed channels are (tanh_c, sigmoid_c) pairs -> Cout/2 outputs
+  CONV_ACCUM = 8,      // y = y_old + v
+};
+enum ConvAct : int { ACT_NONE = 0, ACT_RELU = 1, ACT_MISH = 2, ACT_GELU = 3, ACT_TANH = 4 };
+
+struct ConvParams {
+  const float* x = nullptr;
+  long long sxb = 0, sxc = 0, sxt = 1;  // element strides of x[b, ci, t]
+  const float* w = nullptr;             // packed [Cin][K][CoutPad]
+  int cout_pad = 0;
+  const float* bias = nullptr;          // [Cout] (packed order) or null
+  float* y = nullptr;
+  long long syb = 0, syc = 0, syt = 1;  // element strides of y[b, co, t]
+  const float* res = nullptr;           // residual, indexed like y (same strides), or null
+  const float* addvec = nullptr;        // optional [Tout_total][Cout] row table added after act
+                                        // (Whisper positional embedding), or null
+  const long long* lengths = nullptr;   // [B] int64 or null
+  int B = 0, Cin = 0, Cout = 0, Tin = 0;
+  int K = 1, stride = 1, dil = 1, pad = 0;
+  int q0 = 0, nq = 0;                   // outputs q = q0 .. q0+nq-1; x index = q*stride + j*dil - pad
+  int out_mul = 1, out_off = 0;         // y time index = q*out_mul + out_off
+  int flags = 0;
+  int act = ACT_NONE;
+  float out_div = 0.f;                  // if != 0: v = v / out_div (after accumulate)
+};
+int launch_conv1d(const ConvParams& p, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- snake alias
+int launch_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,
+                       const float* fu, const float* fd, int B, int C, int L, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- norm / attention / small ops
+int launch_layernorm_c(const float* x, const float* r, const float* gamma, const float* beta,
+                       float* y, int B, int C, int T, int gb_batch_stride, float eps,
+                       cudaStream_t s);
+int launch_rel_attention(const float* qkv, const float* ek, const float* ev,
+                         const long long* lengths, float* out, int B, int H, int heads, int window,
+                         int T, cudaStream_t s);
+// y[b,o] = bias[o] + sum_i W[o,i] x[b,i]
+int launch_linear_small(const float* x, const float* W, const float* bias, float* y, int B,
+                        int In, int Out, cudaStream_t s);
+// x[b,c,t] += emb[f0_to_coarse(pit[b,t])][c]   (vits/utils.py:20-33 + models.py:47)
+int launch_pitch_embed_add(float* x, const float* pit, const float* emb, int B, int C, int T,
+                           cudaStream_t s);
+// z_p = (m + eps*exp(logs)) * mask, stats = [B,2C,T] (m | logs)   (models.py:50-51)
+int launch_reparam(const float* stats, const float* eps, const long long* lengths, float* z_p,
+                   int B, int C, int T, cudaStream_t s);
+// coupling layer front: xin [B,C,T] (pre-flip), s [B,C] = snac(spk) (m | v):
+//   y[:, :C/2] = flip(xin)[:, :C/2];  x0n = (x0 - s_m) * exp(-s_v) * mask
+int launch_coupling_pre(const float* xin, const float* s, const long long* lengths, float* y,
+                        float* x0n, int B, int C, int T, cudaStream_t s_);
+// coupling layer back: y[:, C/2:] = (s_m + ((x1 - m) * mask) * exp(s_v)) * mask, x1 = flip(xin)[:, C/2:]
+int launch_coupling_post(const float* xin, const float* s, const float* m, const long long* lengths,
+                         float* y, int B, int C, int T, cudaStream_t s_);
+// WN layer tail (modules.py:196-202): rs [B,2H,T] (or [B,H,T] when last):
+//   not last: x = (x + rs[:, :H]) * mask ; out (+)= rs[:, H:]      last: out (+)= rs ; out *= mask
+int launch_wn_update(float* x, float* out, const float* rs, const long long* lengths, int B, int H,
+                     int T, int first, int last, cudaStream_t s);
+
+// ----------------------------------------------------------------------------- NSF source
+int launch_source(const float* f0, const float* rand_ini, const float* noise, const float* merge_w,
+                  const float* merge_b, float* source, double* scan_ws, int B, int T, int hop,
+                  int n_harm, float sampling_rate, cudaStream_t s);
+size_t source_scan_ws_bytes(int B, int T, int n_harm);
+int launch_source2wav(const float* src, int16_t* out, size_t n, cudaStream_t s);
+
+}  // namespace svcb

@@ -1,0 +1,164 @@
+"""Host-side weight packer: reference checkpoint -> one fp32 device blob + name table.
+
+Runs once at load time (the reference re-materialises weight-norm on every forward because
+svc_inference.py:169 calls nn.Module.eval(), not Generator.eval(inference=True); folding once is
+what vits_decoder/generator.py:154-158 does for inference).  Everything arithmetic here is the
+reference's own parameter algebra (torch._weight_norm, exp of the Snake log-scale parameters);
+the data path never touches the host again.
+
+Packed tensors (all fp32, each 256-byte aligned in the blob):
+
+  <conv>.w   [Cin][K][CoutPad8]  output channel innermost, padded to a multiple of 8
+  <conv>.b   [Cout]
+  flow.<f>.in.<l>.*   output channels interleaved (tanh_c, sigmoid_c) so the WaveNet gate
+                      (vits/commons.py:126-133) is a conv epilogue
+  enc.<i>.qkv.*       conv_q | conv_k | conv_v concatenated along Cout (attentions.py:216-218)
+  dec.ups.<i>.ph<r>.w ConvTranspose1d split into `rate` polyphase sub-filters:
+                      w_r[co][ci][j'] = w[ci][co][r + rate*(M-1-j')], M = ceil(k/rate)
+  dec.res.<n>.act.<a>.ea / .ib   exp(alpha), 1/(exp(beta)+1e-9)   (alias/act.py:85-91)
+  dec.res.<n>.act.<a>.fu / .fd   the 12 up / down taps stored in the checkpoint
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, List, Tuple
+
+import numpy as np
+import torch
+
+ALIGN = 256
+
+
+def fold_weight_norm(sd, prefix: str) -> torch.Tensor:
+    if prefix + ".weight" in sd:
+        return sd[prefix + ".weight"].float()
+    return torch._weight_norm(sd[prefix + ".weight_v"].float(), sd[prefix + ".weight_g"].float(), 0)
+
+
+def pack_conv(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, K] -> [Cin, K, CoutPad8] (zero padded)."""
+    cout, cin, k = w.shape
+    cp = (cout + 7) // 8 * 8
+    out = torch.zeros(cin, k, cp, dtype=torch.float32)
+    out[:, :, :cout] = w.permute(1, 2, 0)
+    return out.contiguous()
+
+
+def config_from_hp(hp, precision: int = 0) -> dict:
+    rates = [int(x) for x in hp.gen.upsample_rates]
+    ks = [int(x) for x in hp.gen.upsample_kernel_sizes]
+    rk = [int(x) for x in hp.gen.resblock_kernel_sizes]
+    rd = [[int(y) for y in x] for x in hp.gen.resblock_dilation_sizes]
+    return dict(
+        ppg_dim=int(hp.vits.ppg_dim), vec_dim=int(hp.vits.vec_dim), spk_dim=int(hp.vits.spk_dim),
+        inter_channels=int(hp.vits.inter_channels), hidden_channels=int(hp.vits.hidden_channels),
+        filter_channels=int(hp.vits.filter_channels),
+        # constants hard-coded by the reference at vits/models.py:220-238
+        enc_layers=6, enc_heads=2, enc_kernel=3, enc_window=4, n_flows=4, wn_layers=4, wn_kernel=5,
+        gen_input=int(hp.gen.upsample_input), gen_initial_channel=int(hp.gen.upsample_initial_channel),
+        n_ups=len(rates), up_rates=rates, up_kernels=ks, n_res=len(rk), res_kernels=rk,
+        res_dilations=rd, sampling_rate=int(hp.data.sampling_rate), n_harmonics=11,
+        precision=int(precision))
+
+
+def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[str, torch.Tensor]]:
+    """Return [(packed_name, fp32 tensor)] in blob order."""
+    out: List[Tuple[str, torch.Tensor]] = []
+
+    def put(name, t):
+        out.append((name, t.detach().float().contiguous()))
+
+    def conv(name, w, b=None):
+        put(name + ".w", pack_conv(w))
+        if b is not None:
+            put(name + ".b", b)
+
+    H = cfg["hidden_channels"]
+    conv("enc_p.pre", sd["enc_p.pre.weight"], sd["enc_p.pre.bias"])
+    conv("enc_p.hub", sd["enc_p.hub.weight"], sd["enc_p.hub.bias"])
+    put("enc_p.pit", sd["enc_p.pit.weight"])
+    for i in range(cfg["enc_layers"]):
+        a = f"enc_p.enc.attn_layers.{i}"
+        wq = torch.cat([sd[f"{a}.conv_{n}.weight"] for n in "qkv"], 0)
+        bq = torch.cat([sd[f"{a}.conv_{n}.bias"] for n in "qkv"], 0)
+        conv(f"enc.{i}.qkv", wq, bq)
+        conv(f"enc.{i}.o", sd[f"{a}.conv_o.weight"], sd[f"{a}.conv_o.bias"])
+        put(f"enc.{i}.ek", sd[f"{a}.emb_rel_k"][0])
+        put(f"enc.{i}.ev", sd[f"{a}.emb_rel_v"][0])
+        put(f"enc.{i}.ln1.g", sd[f"enc_p.enc.norm_layers_1.{i}.gamma"])
+        put(f"enc.{i}.ln1.b", sd[f"enc_p.enc.norm_layers_1.{i}.beta"])
+        f = f"enc_p.enc.ffn_layers.{i}"
+        conv(f"enc.{i}.ffn1", sd[f"{f}.conv_1.weight"], sd[f"{f}.conv_1.bias"])
+        conv(f"enc.{i}.ffn2", sd[f"{f}.conv_2.weight"], sd[f"{f}.conv_2.bias"])
+        put(f"enc.{i}.ln2.g", sd[f"enc_p.enc.norm_layers_2.{i}.gamma"])
+        put(f"enc.{i}.ln2.b", sd[f"enc_p.enc.norm_layers_2.{i}.beta"])
+    conv("enc_p.proj", sd["enc_p.proj.weight"], sd["enc_p.proj.bias"])
+
+    for fidx in range(cfg["n_flows"]):
+        p = f"flow.flows.{2 * fidx}"
+        q = f"flow.{fidx}"
+        conv(q + ".pre", sd[p + ".pre.weight"], sd[p + ".pre.bias"])
+        for l in range(cfg["wn_layers"]):
+            w = fold_weight_norm(sd, f"{p}.enc.in_layers.{l}")
+            b = sd[f"{p}.enc.in_layers.{l}.bias"]
+            idx = torch.stack([torch.arange(H), torch.arange(H) + H], 1).reshape(-1)  # (t0,s0,t1,s1,..)
+            conv(f"{q}.in.{l}", w[idx], b[idx])
+            conv(f"{q}.rs.{l}", fold_weight_norm(sd, f"{p}.enc.res_skip_layers.{l}"),
+                 sd[f"{p}.enc.res_skip_layers.{l}.bias"])
+        conv(q + ".post", sd[p + ".post.weight"], sd[p + ".post.bias"])
+        put(q + ".snac.w", sd[p + ".snac.weight"][:, :, 0])
+        put(q + ".snac.b", sd[p + ".snac.bias"])
+
+    put("dec.adapter.scale.w", sd["dec.adapter.W_scale.weight"])
+    put("dec.adapter.scale.b", sd["dec.adapter.W_scale.bias"])
+    put("dec.adapter.bias.w", sd["dec.adapter.W_bias.weight"])
+    put("dec.adapter.bias.b", sd["dec.adapter.W_bias.bias"])
+    conv("dec.conv_pre", sd["dec.conv_pre.weight"], sd["dec.conv_pre.bias"])
+    put("dec.merge_w", sd["dec.m_source.merge_w"].reshape(-1))
+    put("dec.merge_b", sd["dec.m_source.merge_b"].reshape(-1))
+    for i, (rate, k) in enumerate(zip(cfg["up_rates"], cfg["up_kernels"])):
+        w = fold_weight_norm(sd, f"dec.ups.{i}")  # [Cin, Cout, k]
+        M = (k + rate - 1) // rate
+        for r in range(rate):
+            sub = torch.zeros(w.shape[1], w.shape[0], M)
+            for jp in range(M):
+                j = r + rate * (M - 1 - jp)
+                if j < k:
+                    sub[:, :, jp] = w[:, :, j].t()
+            put(f"dec.ups.{i}.ph{r}.w", pack_conv(sub))
+        put(f"dec.ups.{i}.b", sd[f"dec.ups.{i}.bias"])
+        conv(f"dec.noise.{i}", sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"])
+    n_blocks = cfg["n_ups"] * cfg["n_res"]
+    for n in range(n_blocks):
+        p = f"dec.resblocks.{n}"
+        for d in range(3):
+            conv(f"dec.res.{n}.c1.{d}", fold_weight_norm(sd, f"{p}.convs1.{d}"), sd[f"{p}.convs1.{d}.bias"])
+            conv(f"dec.res.{n}.c2.{d}", fold_weight_norm(sd, f"{p}.convs2.{d}"), sd[f"{p}.convs2.{d}.bias"])
+        for a in range(6):
+            _snake(put, f"dec.res.{n}.act.{a}", sd, f"{p}.activations.{a}")
+    _snake(put, "dec.post.act", sd, "dec.activation_post")
+    conv("dec.conv_post", sd["dec.conv_post.weight"])
+    return out
+
+
+def _snake(put, name, sd, p):
+    put(name + ".ea", torch.exp(sd[p + ".act.alpha"].float()))
+    put(name + ".ib", 1.0 / (torch.exp(sd[p + ".act.beta"].float()) + 1e-9))
+    put(name + ".fu", sd[p + ".upsample.filter"].reshape(-1))
+    put(name + ".fd", sd[p + ".downsample.lowpass.filter"].reshape(-1))
+
+
+def build_blob(items: List[Tuple[str, torch.Tensor]]):
+    """-> (flat fp32 CPU tensor, [(name, offset_bytes, numel)])."""
+    table = []
+    off = 0
+    for name, t in items:
+        off = (off + ALIGN - 1) // ALIGN * ALIGN
+        table.append((name, off, t.numel()))
+        off += t.numel() * 4
+    total = (off + ALIGN - 1) // ALIGN * ALIGN
+    blob = torch.zeros(total // 4, dtype=torch.float32)
+    for (name, o, n), (_, t) in zip(table, items):
+        blob[o // 4:o // 4 + n] = t.reshape(-1)
+    return blob, table
