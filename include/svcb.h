@@ -86,6 +86,9 @@ typedef struct {
 
 const char* svcb_last_error(void);
 int svcb_version(void);
+/* sizeof() of the ABI structs as compiled: 0 svcb_config, 1 svcb_tensor_entry, 2 svcb_taps
+ * (lets a foreign-language binding verify its struct layout at load time). */
+size_t svcb_sizeof(int32_t which);
 
 /* Replaces: SynthesizerInfer.__init__ + load_svc_model (svc_inference.py:61-74,163-170).
  * `dev_blob` holds fp32 tensors already folded/re-laid-out by the host packer
@@ -139,6 +142,13 @@ int svcb_infer(const svcb_model* m, const float* ppg, const float* vec, const fl
 
 /* Number of kernels enqueued by the most recent call on this thread (bench.py's gpu_launches). */
 int64_t svcb_last_launch_count(void);
+
+/* Per-kernel timing for roofline reports: after svcb_timing_enable(1) every launch is bracketed
+ * by CUDA events on its stream; after the caller synchronises, svcb_timing_report() returns
+ * "name launches total_ms algorithmic_flops algorithmic_bytes" lines.  Not thread-safe; off by
+ * default (zero overhead). */
+void svcb_timing_enable(int32_t on);
+const char* svcb_timing_report(void);
 
 /* ---- single-operator entry points (unit-test surface; same kernels the pipeline uses) ---- */
 

@@ -1,0 +1,115 @@
+"""GPU parity of each CUDA operator against the oracle's torch-CPU fp32 arithmetic, called
+through the C ABI.  Tolerances are absolute on O(1) data; fp32 accumulation order differs from
+MKL-DNN's so bit-exactness is not expected (stated per test)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import svc_oracle as O
+from tests.util import max_abs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    from whisper_vits_svc_b200 import ops as o
+    return o
+
+
+CONV_CASES = [
+    # B, Cin, Cout, T, K, stride, dil, pad
+    (2, 192, 192, 300, 1, 1, 1, 0),
+    (2, 192, 384, 301, 5, 1, 1, 2),
+    (1, 160, 160, 1000, 11, 1, 5, 25),
+    (2, 20, 20, 777, 7, 1, 3, 9),
+    (2, 10, 10, 1500, 3, 1, 1, 1),
+    (1, 10, 1, 640, 7, 1, 1, 3),
+    (2, 1, 40, 4096, 8, 4, 1, 2),
+    (1, 1, 160, 12800, 128, 64, 1, 32),
+    (1, 80, 1280, 200, 3, 1, 1, 1),
+    (1, 96, 64, 201, 3, 2, 1, 1),
+    (3, 7, 13, 50, 2, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv1d(ops, case):
+    B, Cin, Cout, T, K, s, d, p = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = torch.randn(B, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv1d(x, w, b, stride=s, padding=p, dilation=d)
+    got = ops.conv1d(x.cuda(), w, b.cuda(), stride=s, padding=p, dilation=d)
+    assert got.shape == ref.shape
+    assert max_abs(got, ref) <= 2e-5  # fp32, different summation order
+
+
+@pytest.mark.parametrize("act,fn", [(1, torch.relu), (2, lambda v: v * torch.tanh(F.softplus(v))),
+                                    (3, F.gelu), (4, torch.tanh)])
+def test_conv1d_activations(ops, act, fn):
+    g = torch.Generator().manual_seed(act)
+    x = torch.randn(2, 24, 100, generator=g) * 3
+    w = torch.randn(16, 24, 3, generator=g) / 4
+    b = torch.randn(16, generator=g)
+    ref = fn(F.conv1d(x, w, b, padding=1))
+    got = ops.conv1d(x.cuda(), w, b.cuda(), padding=1, act=act)
+    assert max_abs(got, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("C,L", [(10, 3000), (160, 1024), (3, 1), (5, 7), (20, 2049)])
+def test_snake_alias(ops, sd, C, L):
+    g = torch.Generator().manual_seed(C + L)
+    x = torch.randn(2, C, L, generator=g) * 2
+    fake = {"a.act.alpha": torch.randn(C, generator=g) * 0.5, "a.act.beta": torch.randn(C, generator=g) * 0.5,
+            "a.upsample.filter": sd["dec.activation_post.upsample.filter"],
+            "a.downsample.lowpass.filter": sd["dec.activation_post.downsample.lowpass.filter"]}
+    ref = O.snake_alias(fake, "a", x)
+    got = ops.snake_alias(x.cuda(), fake["a.act.alpha"], fake["a.act.beta"], fake["a.upsample.filter"],
+                          fake["a.downsample.lowpass.filter"])
+    assert max_abs(got, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("C,T,per_batch", [(192, 333, False), (192, 64, True), (80, 31, True)])
+def test_layernorm_c(ops, C, T, per_batch):
+    g = torch.Generator().manual_seed(C + T)
+    x = torch.randn(3, C, T, generator=g) * 2 + 0.5
+    r = torch.randn(3, C, T, generator=g)
+    if per_batch:
+        gamma, beta = torch.randn(3, C, generator=g), torch.randn(3, C, generator=g)
+        xt = x.transpose(1, -1)
+        mean = xt.mean(-1, keepdim=True)
+        var = ((xt - mean) ** 2).mean(-1, keepdim=True)
+        ref = (((xt - mean) / (var + 1e-5).sqrt()) * gamma.unsqueeze(1) + beta.unsqueeze(1)).transpose(1, -1)
+        got = ops.layernorm_c(x.cuda(), None, gamma.cuda(), beta.cuda())
+    else:
+        gamma, beta = torch.randn(C, generator=g), torch.randn(C, generator=g)
+        ref = O.channel_layer_norm(x + r, gamma, beta)
+        got = ops.layernorm_c(x.cuda(), r.cuda(), gamma.cuda(), beta.cuda())
+    assert max_abs(got, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("T,lens", [(150, [150, 97]), (64, [64, 64]), (65, [65, 1]), (300, [300, 201])])
+def test_rel_attention(ops, T, lens):
+    g = torch.Generator().manual_seed(T)
+    H, heads, w = 192, 2, 4
+    B = len(lens)
+    x = torch.randn(B, H, T, generator=g)
+    fake = {}
+    for n in "qkvo":
+        fake[f"a.conv_{n}.weight"] = torch.randn(H, H, 1, generator=g) / H ** 0.5 * 1.5
+        fake[f"a.conv_{n}.bias"] = torch.randn(H, generator=g) * 0.1
+    fake["a.emb_rel_k"] = torch.randn(1, 9, H // heads, generator=g) * (H // heads) ** -0.5
+    fake["a.emb_rel_v"] = torch.randn(1, 9, H // heads, generator=g) * (H // heads) ** -0.5
+    lengths = torch.tensor(lens)
+    mask = O.sequence_mask(lengths, T).unsqueeze(1).float()
+    attn_mask = mask.unsqueeze(2) * mask.unsqueeze(-1)
+    # oracle applies conv_o at the end; undo by making it identity for this unit test
+    fake["a.conv_o.weight"] = torch.eye(H).unsqueeze(-1)
+    fake["a.conv_o.bias"] = torch.zeros(H)
+    ref = O.rel_attention(fake, "a", x, attn_mask)
+    qkv = torch.cat([F.conv1d(x, fake[f"a.conv_{n}.weight"], fake[f"a.conv_{n}.bias"]) for n in "qkv"], 1)
+    got = ops.rel_attention(qkv.cuda(), fake["a.emb_rel_k"].cuda(), fake["a.emb_rel_v"].cuda(), lengths)
+    assert max_abs(got, ref) <= 2e-5

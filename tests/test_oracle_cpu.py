@@ -1,0 +1,82 @@
+"""CPU tests: the oracle against the committed golden fixtures (generated from the unmodified
+reference by oracle/make_golden.py) and, when the reference tree is present, against the
+reference itself."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_import, svc_oracle as O
+from tests.util import GOLDEN, make_inputs, max_abs
+from whisper_vits_svc_b200 import hparams, synth
+
+FULL = ["infer_b2_t48", "infer_b3_t70_ragged"]
+
+
+def _load(name):
+    return np.load(os.path.join(GOLDEN, name + ".npz"))
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_oracle_matches_golden_full(name, hp, sd):
+    g = _load(name)
+    d = make_inputs(int(g["seed"]), int(g["B"]), int(g["T"]), hp, ragged=bool(g["ragged"]))
+    src = O.pitch2source(sd, hp, d["pit"], d["rand_ini"], d["noise"])
+    assert max_abs(src, g["source"]) <= 1e-6
+    st = {}
+    wave = O.synthesizer_infer(sd, hp, d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, d["eps"], stages=st)
+    assert max_abs(st["z_p"], g["z_p"]) <= 1e-5
+    assert max_abs(st["z"], g["z"]) <= 1e-5
+    assert max_abs(wave, g["wave"]) <= 1e-5
+    assert np.array_equal(O.source2wav(src[:1]), g["pcm"])
+
+
+@pytest.mark.parametrize("name,over", [("gen80_b2_t36", dict(gen__upsample_input=80, data__sampling_rate=24000)),
+                                       ("gen192_b1_t64", {})])
+def test_oracle_matches_golden_generator(name, over, hp):
+    g = _load(name)
+    hpx = hparams.override(hp, **over)
+    sdx = synth.svc_state_dict(hpx, 1234)
+    d = make_inputs(int(g["seed"]), int(g["B"]), int(g["T"]), hpx, gen_only=True)
+    src = O.pitch2source(sdx, hpx, d["pit"], d["rand_ini"], d["noise"])
+    assert max_abs(src, g["source"]) <= 1e-6
+    wave = O.generator(sdx, hpx, d["spk"], d["z"], src)
+    assert max_abs(wave, g["wave"]) <= 1e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_matches_reference_live(hp, sd):
+    from oracle.make_golden import FeedRNG, ref_model
+    m = ref_model(hp, sd)
+    d = make_inputs(77, 2, 33, hp, ragged=True)
+    with torch.no_grad(), FeedRNG([d["rand_ini"]], [d["noise"], d["eps"]]):
+        src = m.pitch2source(d["pit"])
+        wave = m.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src)
+    src_o = O.pitch2source(sd, hp, d["pit"], d["rand_ini"], d["noise"])
+    wave_o = O.synthesizer_infer(sd, hp, d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src_o, d["eps"])
+    assert max_abs(src, src_o) <= 1e-6
+    assert max_abs(wave, wave_o) <= 1e-6
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_synthetic_checkpoint_has_reference_keys(hp, sd):
+    Syn = ref_import.import_synthesizer()
+    ref_sd = Syn(513, 25, ref_import.to_attr(hp)).state_dict()
+    assert set(ref_sd) == set(sd)
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(sd[k].shape), k
+    # the alias-filter buffers are the reference's own Kaiser-sinc taps
+    assert torch.equal(ref_sd["dec.activation_post.upsample.filter"], sd["dec.activation_post.upsample.filter"])
+
+
+def test_f0_to_coarse_integer_hz_is_rounding_safe():
+    """The CUDA path evaluates the mel mapping in fp32 with a correctly rounded log; for every
+    integer-Hz pitch (the reference's CSV format) that equals torch's fp32 result."""
+    f = torch.arange(0, 1101, dtype=torch.float32)
+    ref = O.f0_to_coarse(f)
+    mel = 1127 * torch.log((1 + f / 700).double()).float()
+    mel = torch.where(mel > 0, (mel - np.float32(77.75496616579426)) * 254 / np.float32(986.6532670978451) + 1, mel)
+    mel = mel.clamp(min=1.0, max=255.0)
+    assert torch.equal((mel + 0.5).long(), ref)
+    assert ref.min() >= 1 and ref.max() <= 255

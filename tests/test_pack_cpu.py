@@ -1,0 +1,71 @@
+"""Host packer: the re-laid-out weights mean what the kernels assume (checked with torch on CPU)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from whisper_vits_svc_b200 import pack
+
+
+def unpack_conv(wp, cout):
+    return wp[:, :, :cout].permute(2, 0, 1).contiguous()  # [Cin,K,CoutPad] -> [Cout,Cin,K]
+
+
+def test_pack_conv_roundtrip():
+    w = torch.randn(20, 7, 3)
+    wp = pack.pack_conv(w)
+    assert wp.shape == (7, 3, 24) and torch.equal(unpack_conv(wp, 20), w)
+    assert torch.count_nonzero(wp[:, :, 20:]) == 0
+
+
+@pytest.mark.parametrize("k,s", [(15, 5), (8, 4), (4, 2), (7, 3), (16, 8)])
+def test_polyphase_transposed_conv(k, s):
+    """ConvTranspose1d == `rate` stride-1 sub-convolutions written with output stride `rate`
+    (csrc/api.cu run_generator uses exactly these q0 / nq / out_off formulas)."""
+    torch.manual_seed(k * 10 + s)
+    cin, cout, T = 6, 4, 23
+    w = torch.randn(cin, cout, k)
+    b = torch.randn(cout)
+    x = torch.randn(2, cin, T)
+    p = (k - s) // 2
+    ref = F.conv_transpose1d(x, w, b, stride=s, padding=p)
+    Lout = ref.shape[-1]
+    M = (k + s - 1) // s
+    y = torch.zeros_like(ref)
+    for r in range(s):
+        sub = torch.zeros(cout, cin, M)
+        for jp in range(M):
+            j = r + s * (M - 1 - jp)
+            if j < k:
+                sub[:, :, jp] = w[:, :, j].t()
+        pr = p - r
+        q0 = (pr + s - 1) // s if pr > 0 else 0
+        qmax = (Lout - 1 + p - r) // s
+        nq = qmax - q0 + 1
+        # generic kernel semantics: out[q] = sum_j x[q + j - (M-1)] * sub[j], zero outside [0,T)
+        xp = F.pad(x, (M - 1 + 8, M + 8))
+        full = F.conv1d(xp, sub, b)  # full[i] <-> q = i - 8
+        for t in range(nq):
+            q = q0 + t
+            y[:, :, q * s + r - p] = full[:, :, q + 8]
+    assert torch.allclose(y, ref, atol=1e-5), (y - ref).abs().max()
+
+
+def test_packed_model_tensor_inventory(hp, sd):
+    cfg = pack.config_from_hp(hp)
+    items = dict(pack.pack_svc_state_dict(sd, cfg))
+    # gate interleave: packed channel 2c is tanh row c, 2c+1 is sigmoid row c
+    H = cfg["hidden_channels"]
+    w = pack.fold_weight_norm(sd, "flow.flows.0.enc.in_layers.0")
+    wp = unpack_conv(items["flow.0.in.0.w"], 2 * H)
+    assert torch.equal(wp[0::2], w[:H]) and torch.equal(wp[1::2], w[H:])
+    # qkv concat
+    q = unpack_conv(items["enc.0.qkv.w"], 3 * H)
+    assert torch.equal(q[H:2 * H], sd["enc_p.enc.attn_layers.0.conv_k.weight"])
+    # snake parameters
+    ea = items["dec.res.0.act.0.ea"]
+    assert torch.allclose(ea, torch.exp(sd["dec.resblocks.0.activations.0.act.alpha"]))
+    blob, table = pack.build_blob(list(items.items()))
+    assert all(off % 256 == 0 for _, off, _ in table)
+    name, off, n = table[5]
+    assert torch.equal(blob[off // 4: off // 4 + n], items[name].reshape(-1))

@@ -68,7 +68,10 @@ class Taps(ctypes.Structure):
 SIGNATURES = {
     "svcb_last_error": (c_char_p, []),
     "svcb_version": (c_int, []),
+    "svcb_sizeof": (c_size_t, [c_int32]),
     "svcb_last_launch_count": (c_int64, []),
+    "svcb_timing_enable": (None, [c_int32]),
+    "svcb_timing_report": (c_char_p, []),
     "svcb_model_create": (c_int, [c_void_p, c_size_t, POINTER(TensorEntry), c_int32, POINTER(Config), POINTER(c_void_p)]),
     "svcb_model_destroy": (None, [c_void_p]),
     "svcb_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
@@ -101,6 +104,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
+    for which, st in enumerate((Config, TensorEntry, Taps)):
+        if lib.svcb_sizeof(which) != ctypes.sizeof(st):
+            raise SvcbError(f"ABI struct {st.__name__} size mismatch: C {lib.svcb_sizeof(which)} vs ctypes {ctypes.sizeof(st)}")
     _lib = lib
     return lib
 

@@ -15,6 +15,26 @@ static thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch() { ++g_launches; }
 
+// ----------------------------------------------------------------------------- kernel timing
+struct TimedLaunch { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
+static bool g_timing = false;
+static std::vector<TimedLaunch> g_timed;
+static std::string g_report;
+
+KernelScope::KernelScope(const char* name, cudaStream_t s, double flops, double bytes)
+    : slot(-1), stream(s) {
+  if (!g_timing) return;
+  TimedLaunch t;
+  t.name = name; t.flops = flops; t.bytes = bytes;
+  if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return;
+  cudaEventRecord(t.e0, s);
+  g_timed.push_back(t);
+  slot = (int)g_timed.size() - 1;
+}
+KernelScope::~KernelScope() {
+  if (slot >= 0) cudaEventRecord(g_timed[slot].e1, stream);
+}
+
 struct ConvW {
   const float* w = nullptr;
   const float* b = nullptr;
@@ -128,6 +148,7 @@ __global__ void mask_mul_kernel(float* __restrict__ x, const long long* __restri
 }
 static int launch_mask_mul(float* x, const long long* lengths, int B, int C, int T, cudaStream_t s) {
   dim3 grid((T + 127) / 128, C, B);
+  KernelScope ks("mask_mul", s, 0.0, 4.0 * B * C * (double)T);
   mask_mul_kernel<<<grid, 128, 0, s>>>(x, lengths, C, T);
   SVCB_LAUNCH_CHECK("mask_mul");
   return SVCB_OK;
@@ -482,7 +503,44 @@ extern "C" {
 
 const char* svcb_last_error(void) { return g_err.c_str(); }
 int svcb_version(void) { return 100; }
+size_t svcb_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return sizeof(svcb_config);
+    case 1: return sizeof(svcb_tensor_entry);
+    case 2: return sizeof(svcb_taps);
+    default: return 0;
+  }
+}
 int64_t svcb_last_launch_count(void) { return g_launches; }
+
+void svcb_timing_enable(int32_t on) {
+  g_timing = on != 0;
+  if (on) {
+    for (auto& t : g_timed) { cudaEventDestroy(t.e0); cudaEventDestroy(t.e1); }
+    g_timed.clear();
+  }
+}
+
+const char* svcb_timing_report(void) {
+  // caller must have synchronised the stream(s); one line per kernel name:
+  // name launches total_ms total_flops total_bytes
+  struct Agg { long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& t : g_timed) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, t.e0, t.e1) != cudaSuccess) continue;
+    Agg& a = agg[t.name];
+    a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes;
+  }
+  g_report.clear();
+  char buf[256];
+  for (auto& kv : agg) {
+    snprintf(buf, sizeof(buf), "%s %ld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+             kv.second.flops, kv.second.bytes);
+    g_report += buf;
+  }
+  return g_report.c_str();
+}
 
 int svcb_model_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host,
                       int32_t n_entries, const svcb_config* cfg_host, svcb_model** out) {

@@ -11,6 +11,15 @@ namespace svcb {
 void set_error(const std::string& msg);
 void count_launch();
 
+// Optional per-kernel CUDA-event timing (svcb_timing_enable): a KernelScope brackets one launch
+// with two events on the launching stream and books its algorithmic FLOPs / bytes under `name`.
+struct KernelScope {
+  KernelScope(const char* name, cudaStream_t s, double flops, double bytes);
+  ~KernelScope();
+  int slot;
+  cudaStream_t stream;
+};
+
 #define SVCB_CUDA_CHECK(expr)                                                            \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

@@ -69,6 +69,7 @@ int launch_layernorm_c(const float* x, const float* r, const float* gamma, const
     attr = true;
   }
   dim3 grid((T + 31) / 32, B), block(32, 8);
+  KernelScope ks("layernorm_c", s, 8.0 * B * C * (double)T, 4.0 * B * C * (double)T * (r ? 3 : 2));
   layernorm_c_kernel<<<grid, block, smem, s>>>(x, r, gamma, beta, y, C, T, gb_batch_stride, eps);
   SVCB_LAUNCH_CHECK("layernorm_c");
   return SVCB_OK;
@@ -271,6 +272,7 @@ int launch_rel_attention(const float* qkv, const float* ek, const float* ev,
     attr = true;
   }
   dim3 grid((T + RA_BQ - 1) / RA_BQ, heads, B);
+  KernelScope ks("rel_attention", s, 4.0 * B * H * (double)T * T, 16.0 * B * H * (double)T);
   rel_attention_kernel<96><<<grid, 256, smem, s>>>(qkv, ek, ev, lengths, out, H, heads, window, T);
   SVCB_LAUNCH_CHECK("rel_attention");
   return SVCB_OK;
@@ -294,6 +296,7 @@ __global__ void linear_small_kernel(const float* __restrict__ x, const float* __
 int launch_linear_small(const float* x, const float* W, const float* bias, float* y, int B, int In,
                         int Out, cudaStream_t s) {
   dim3 block(32, 8), grid((Out + 7) / 8, B);
+  KernelScope ks("linear_small", s, 2.0 * B * In * Out, 4.0 * ((double)In * Out + B * (In + Out)));
   linear_small_kernel<<<grid, block, 0, s>>>(x, W, bias, y, In, Out);
   SVCB_LAUNCH_CHECK("linear_small");
   return SVCB_OK;
@@ -324,6 +327,7 @@ __global__ void pitch_embed_add_kernel(float* __restrict__ x, const float* __res
 int launch_pitch_embed_add(float* x, const float* pit, const float* emb, int B, int C, int T,
                            cudaStream_t s) {
   dim3 grid((T + 127) / 128, 16, B);
+  KernelScope ks("pitch_embed_add", s, 0.0, 12.0 * B * C * (double)T);
   pitch_embed_add_kernel<<<grid, 128, 0, s>>>(x, pit, emb, C, T);
   SVCB_LAUNCH_CHECK("pitch_embed_add");
   return SVCB_OK;
@@ -344,6 +348,7 @@ __global__ void reparam_kernel(const float* __restrict__ stats, const float* __r
 int launch_reparam(const float* stats, const float* eps, const long long* lengths, float* z_p, int B,
                    int C, int T, cudaStream_t s) {
   dim3 grid((T + 127) / 128, C, B);
+  KernelScope ks("reparam", s, 0.0, 16.0 * B * C * (double)T);
   reparam_kernel<<<grid, 128, 0, s>>>(stats, eps, lengths, z_p, C, T);
   SVCB_LAUNCH_CHECK("reparam");
   return SVCB_OK;
@@ -367,6 +372,7 @@ __global__ void coupling_pre_kernel(const float* __restrict__ xin, const float* 
 int launch_coupling_pre(const float* xin, const float* sp, const long long* lengths, float* y,
                         float* x0n, int B, int C, int T, cudaStream_t s) {
   dim3 grid((T + 127) / 128, C / 2, B);
+  KernelScope ks("coupling_pre", s, 0.0, 6.0 * B * C * (double)T);
   coupling_pre_kernel<<<grid, 128, 0, s>>>(xin, sp, lengths, y, x0n, C, T);
   SVCB_LAUNCH_CHECK("coupling_pre");
   return SVCB_OK;
@@ -391,6 +397,7 @@ __global__ void coupling_post_kernel(const float* __restrict__ xin, const float*
 int launch_coupling_post(const float* xin, const float* sp, const float* m, const long long* lengths,
                          float* y, int B, int C, int T, cudaStream_t s) {
   dim3 grid((T + 127) / 128, C / 2, B);
+  KernelScope ks("coupling_post", s, 0.0, 6.0 * B * C * (double)T);
   coupling_post_kernel<<<grid, 128, 0, s>>>(xin, sp, m, lengths, y, C, T);
   SVCB_LAUNCH_CHECK("coupling_post");
   return SVCB_OK;
@@ -418,6 +425,7 @@ __global__ void wn_update_kernel(float* __restrict__ x, float* __restrict__ out,
 int launch_wn_update(float* x, float* out, const float* rs, const long long* lengths, int B, int H,
                      int T, int first, int last, cudaStream_t s) {
   dim3 grid((T + 127) / 128, H, B);
+  KernelScope ks("wn_update", s, 0.0, 24.0 * B * H * (double)T);
   wn_update_kernel<<<grid, 128, 0, s>>>(x, out, rs, lengths, H, T, first, last);
   SVCB_LAUNCH_CHECK("wn_update");
   return SVCB_OK;

@@ -71,6 +71,7 @@ int launch_snake_alias(const float* x, float* y, const float* ea, const float* i
   if (B <= 0 || C <= 0 || L <= 0) return SVCB_OK;
   if (C > 65535 || B > 65535) { set_error("snake_alias: C or B exceeds grid limits"); return SVCB_E_BAD_SHAPE; }
   dim3 grid((L + SA_TL - 1) / SA_TL, C, B);
+  KernelScope ks("snake_alias", s, 70.0 * B * C * (double)L, 8.0 * B * C * (double)L);
   snake_alias_kernel<<<grid, 256, 0, s>>>(x, y, ea, inv_b, fu, fd, C, L);
   SVCB_LAUNCH_CHECK("snake_alias");
   return SVCB_OK;

@@ -96,11 +96,15 @@ int launch_source(const float* f0, const float* rand_ini, const float* noise, co
                   int n_harm, float sampling_rate, cudaStream_t s) {
   if (B <= 0 || T <= 0) return SVCB_OK;
   const int nth = B * n_harm;
-  source_scan_kernel<<<(nth + 63) / 64, 64, 0, s>>>(f0, rand_ini, scan_ws, B, T, hop, n_harm,
-                                                    sampling_rate);
-  SVCB_LAUNCH_CHECK("source_scan");
+  {
+    KernelScope ks("source_scan", s, 0.0, 24.0 * nth * T);
+    source_scan_kernel<<<(nth + 63) / 64, 64, 0, s>>>(f0, rand_ini, scan_ws, B, T, hop, n_harm,
+                                                      sampling_rate);
+    SVCB_LAUNCH_CHECK("source_scan");
+  }
   const long long L = (long long)T * hop;
   dim3 grid((unsigned)((L + 255) / 256), B);
+  KernelScope ks("source_sample", s, 0.0, 4.0 * B * (double)L * (n_harm + 1));
   source_sample_kernel<<<grid, 256, 0, s>>>(f0, noise, merge_w, merge_b, scan_ws, source, B, T, hop,
                                             n_harm, sampling_rate);
   SVCB_LAUNCH_CHECK("source_sample");
@@ -118,6 +122,7 @@ __global__ void source2wav_kernel(const float* __restrict__ src, int16_t* __rest
 
 int launch_source2wav(const float* src, int16_t* out, size_t n, cudaStream_t s) {
   if (n == 0) return SVCB_OK;
+  KernelScope ks("source2wav", s, 0.0, 6.0 * (double)n);
   source2wav_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(src, out, n);
   SVCB_LAUNCH_CHECK("source2wav");
   return SVCB_OK;

@@ -1,0 +1,73 @@
+"""Single-operator entry points of the C ABI on torch CUDA tensors (unit tests / profiling).
+The same kernels the stage pipelines launch; no fallback."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib, pack
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _c(t):
+    assert t.is_cuda, "operators run on CUDA tensors only"
+    return t.float().contiguous()
+
+
+def conv1d(x, weight, bias=None, stride=1, padding=0, dilation=1, act=0):
+    """weight in torch layout [Cout,Cin,K]; packed here (host) then run on the device."""
+    x = _c(x)
+    B, Cin, Tin = x.shape
+    Cout, _, K = weight.shape
+    wp = pack.pack_conv(weight.detach().cpu().float()).to(x.device)
+    b = _c(bias) if bias is not None else None
+    Tout = (Tin + 2 * padding - dilation * (K - 1) - 1) // stride + 1
+    y = torch.empty(B, Cout, Tout, device=x.device)
+    st = _lib.load().svcb_op_conv1d(x.data_ptr(), wp.data_ptr(), b.data_ptr() if b is not None else None,
+                                    y.data_ptr(), B, Cin, Cout, Tin, K, stride, dilation, padding, act, _s())
+    _lib.check(st, "svcb_op_conv1d")
+    return y
+
+
+def snake_alias(x, alpha, beta, fu, fd):
+    x = _c(x)
+    B, C, L = x.shape
+    ea = _c(torch.exp(alpha.float().cpu()).to(x.device))
+    ib = _c((1.0 / (torch.exp(beta.float().cpu()) + 1e-9)).to(x.device))
+    fu, fd = _c(fu.reshape(-1).to(x.device)), _c(fd.reshape(-1).to(x.device))
+    y = torch.empty_like(x)
+    st = _lib.load().svcb_op_snake_alias(x.data_ptr(), y.data_ptr(), ea.data_ptr(), ib.data_ptr(),
+                                         fu.data_ptr(), fd.data_ptr(), B, C, L, _s())
+    _lib.check(st, "svcb_op_snake_alias")
+    return y
+
+
+def layernorm_c(x, r, gamma, beta, eps=1e-5):
+    x = _c(x)
+    B, C, T = x.shape
+    gamma, beta = _c(gamma), _c(beta)
+    stride = C if gamma.dim() == 2 else 0
+    r_ = _c(r) if r is not None else None
+    y = torch.empty_like(x)
+    st = _lib.load().svcb_op_layernorm_c(x.data_ptr(), r_.data_ptr() if r_ is not None else None,
+                                         gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), B, C, T, stride,
+                                         eps, _s())
+    _lib.check(st, "svcb_op_layernorm_c")
+    return y
+
+
+def rel_attention(qkv, emb_k, emb_v, lengths, heads=2, window=4):
+    qkv = _c(qkv)
+    B, H3, T = qkv.shape
+    H = H3 // 3
+    ek, ev = _c(emb_k.reshape(2 * window + 1, -1)), _c(emb_v.reshape(2 * window + 1, -1))
+    lengths = lengths.to(qkv.device, torch.int64).contiguous()
+    out = torch.empty(B, H, T, device=qkv.device)
+    st = _lib.load().svcb_op_rel_attention(qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), lengths.data_ptr(),
+                                           out.data_ptr(), B, H, heads, window, T, _s())
+    _lib.check(st, "svcb_op_rel_attention")
+    return out
