@@ -110,6 +110,17 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def cpu_threads() -> int:
+    """Threads for the CPU arm.  torch's intra-op pool over-subscribes badly on the many tiny
+    depthwise convolutions of this path: on the 128-core GPU-box host 128 threads ran 60x slower
+    than 8 (gpurun_out of round 1), so the arm uses the count that is fastest in practice, capped
+    by what the box has; SVCB_CPU_THREADS overrides."""
+    env = os.environ.get("SVCB_CPU_THREADS")
+    if env:
+        return max(1, int(env))
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
 def synth_inputs(hp, B, T, seed):
     from tests.util import make_inputs
     return make_inputs(seed, B, T, hp)
@@ -134,7 +145,7 @@ def run_reference(args, hp, sd):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    cores = cpu_threads()
     torch.set_num_threads(cores)
     T = 250  # bounded sample: one 2.5 s utterance per step (CPU throughput is length-independent)
     hop = int(np.prod(list(hp.gen.upsample_rates)))
@@ -277,13 +288,13 @@ def run_ours(args, hp, sd):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
+        cores = cpu_threads()
         torch.set_num_threads(cores)
-        Tc = 500
+        Tc = 250
         cpu_reference_run(hp, sd, 50, 1)  # warm-up of the oneDNN primitives
         sec = cpu_reference_run(hp, sd, Tc, 2)
         cpu = {"value": Tc * hop / sec, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"best of 2 x one {Tc / 100:.0f} s utterance (same per-item workload), oracle port of the "
+               "sample": f"best of 2 x one {Tc / 100:.1f} s utterance (same per-item workload), oracle port of the "
                          f"reference CPU path, torch fp32, {cores} threads, {sec:.2f} s"}
 
     if rank == 0:

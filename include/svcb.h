@@ -55,7 +55,8 @@ typedef struct {
   int32_t res_dilations[SVCB_MAX_RES][3];
   int32_t sampling_rate;
   int32_t n_harmonics;   /* 11 = fundamental + 10 overtones (vits_decoder/nsf.py:368) */
-  int32_t precision;     /* 0 = fp32-parity (fp32 FMA / bf16x3 split MMA), 1 = bf16 MMA */
+  int32_t precision;     /* AMP-block convs: 0 = fp32 CUDA cores, 3 = bf16x3 split tcgen05 MMA
+                          * (parity grade), 1 = plain bf16 tcgen05 MMA */
 } svcb_config;
 
 /* One named tensor inside the packed weight blob (host-side table, read at create time). */
@@ -177,6 +178,19 @@ int svcb_op_layernorm_c(const float* x, const float* r, const float* gamma, cons
 int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
                           const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
                           int32_t window, int32_t T, svcb_stream stream);
+
+/* One fused `SnakeAlias -> Conv1d(C->C, K, dilation, same padding) + bias (+ res)` link of
+ * AMPBlock.forward (vits_decoder/bigv.py:50-58) on the tensor cores.  w_tc = pack.py:pack_conv_tc
+ * image; nsplit 1 = bf16, 3 = bf16x3 (parity grade). */
+int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float* ea, const float* inv_b,
+                        const float* fu, const float* fd, const void* w_tc, const float* bias, int32_t B,
+                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit,
+                        svcb_stream stream);
+
+/* Self-test of the tcgen05/TMEM plumbing: D[128,N] = A[shift:shift+128, :K] . B[N,K]^T with
+ * bf16 operands (row-major, device) and fp32 accumulation in tensor memory. */
+int svcb_op_tc_gemm_selftest(const void* A_bf16, const void* B_bf16, float* D, int32_t R, int32_t N,
+                             int32_t K, int32_t shift, svcb_stream stream);
 
 #ifdef __cplusplus
 }

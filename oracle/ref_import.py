@@ -78,6 +78,10 @@ def import_whisper_model():
     _stub("librosa")
     _stub("librosa.filters")
     sys.modules["librosa"].filters = sys.modules["librosa.filters"]
+    if not hasattr(sys.modules["librosa.filters"], "mel"):
+        def _no_mel(*a, **k):
+            raise RuntimeError("librosa is not installed; the log-mel front-end is outside the oracle's scope")
+        sys.modules["librosa.filters"].mel = _no_mel
     import whisper.model as wm  # noqa
     return wm
 

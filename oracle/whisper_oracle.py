@@ -1,0 +1,67 @@
+"""CPU oracle for the PPG extractor (TEST INFRASTRUCTURE): torch-CPU fp32 restatement of the
+truncated Whisper AudioEncoder the reference runs (whisper/model.py:132-163 with the loader's
+surgery, whisper/inference.py:11-29: decoder deleted, last quarter of the encoder blocks deleted,
+ln_post kept).  Consumes the reference checkpoint format {"dims", "model_state_dict"}.
+
+Parity status: pinned by importing the reference (tests/test_oracle_cpu.py, oracle/make_golden.py);
+the reference ships no golden vectors for this path."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
+    """whisper/model.py:48-54"""
+    inc = np.log(max_timescale) / (channels // 2 - 1)
+    inv = torch.exp(-inc * torch.arange(channels // 2))
+    t = torch.arange(length)[:, None] * inv[None, :]
+    return torch.cat([torch.sin(t), torch.cos(t)], dim=1)
+
+
+def kept_layers(dims: dict) -> int:
+    """whisper/inference.py:17-19: del encoder.blocks[-(n // 4):]"""
+    n = dims["n_audio_layer"]
+    return n - n // 4
+
+
+def attention(sd, p, x, n_head):
+    """MultiHeadAttention.forward/qkv_attention, whisper/model.py:66-101 (self-attention, no mask)."""
+    q = F.linear(x, sd[p + ".query.weight"], sd[p + ".query.bias"])
+    k = F.linear(x, sd[p + ".key.weight"])
+    v = F.linear(x, sd[p + ".value.weight"], sd[p + ".value.bias"])
+    b, t, d = q.shape
+    scale = (d // n_head) ** -0.25
+    q = q.view(b, t, n_head, -1).permute(0, 2, 1, 3) * scale
+    k = k.view(b, t, n_head, -1).permute(0, 2, 3, 1) * scale
+    v = v.view(b, t, n_head, -1).permute(0, 2, 1, 3)
+    w = F.softmax((q @ k).float(), dim=-1).to(q.dtype)
+    o = (w @ v).permute(0, 2, 1, 3).flatten(start_dim=2)
+    return F.linear(o, sd[p + ".out.weight"], sd[p + ".out.bias"])
+
+
+def audio_encoder(ckpt: dict, mel: torch.Tensor, stages: dict | None = None) -> torch.Tensor:
+    """AudioEncoder.forward, whisper/model.py:144-163, on mel [B, n_mels, n] -> [B, ceil(n/2), D]."""
+    dims, sd = ckpt["dims"], ckpt["model_state_dict"]
+    D, H = dims["n_audio_state"], dims["n_audio_head"]
+    with torch.no_grad():
+        x = F.gelu(F.conv1d(mel, sd["encoder.conv1.weight"], sd["encoder.conv1.bias"], padding=1))
+        x = F.gelu(F.conv1d(x, sd["encoder.conv2.weight"], sd["encoder.conv2.bias"], stride=2, padding=1))
+        x = x.permute(0, 2, 1)
+        assert x.shape[1] <= dims["n_audio_ctx"], "incorrect audio shape"
+        x = x + sinusoids(dims["n_audio_ctx"], D)[: x.shape[1]]
+        if stages is not None:
+            stages["stem"] = x
+        for i in range(kept_layers(dims)):
+            b = f"encoder.blocks.{i}"
+            h = F.layer_norm(x, (D,), sd[b + ".attn_ln.weight"], sd[b + ".attn_ln.bias"])
+            x = x + attention(sd, b + ".attn", h, H)
+            h = F.layer_norm(x, (D,), sd[b + ".mlp_ln.weight"], sd[b + ".mlp_ln.bias"])
+            h = F.gelu(F.linear(h, sd[b + ".mlp.0.weight"], sd[b + ".mlp.0.bias"]))
+            x = x + F.linear(h, sd[b + ".mlp.2.weight"], sd[b + ".mlp.2.bias"])
+            if stages is not None:
+                stages[f"block{i}"] = x
+        return F.layer_norm(x, (D,), sd["encoder.ln_post.weight"], sd["encoder.ln_post.bias"])

@@ -1,0 +1,113 @@
+"""Host logic (no GPU): chunk arithmetic, wire formats, sharding, 2-rank gloo broadcast."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+
+from tests.util import ROOT
+from whisper_vits_svc_b200 import hostio, shard
+
+
+def _reference_chunks(all_frame, hop_size):
+    """Transliteration of the while-loop of svc_inference.py:94-131 (indices only)."""
+    hop_frame, out_chunk, out_index, res = 10, 2500, 0, []
+    while out_index < all_frame:
+        if out_index == 0:
+            cut_s, cut_s_out = 0, 0
+        else:
+            cut_s, cut_s_out = out_index - hop_frame, hop_frame * hop_size
+        if out_index + out_chunk + hop_frame > all_frame:
+            cut_e, cut_e_out = all_frame, -1
+        else:
+            cut_e, cut_e_out = out_index + out_chunk + hop_frame, -1 * hop_frame * hop_size
+        res.append((cut_s, cut_e, cut_s_out, cut_e_out))
+        out_index += out_chunk
+    return res
+
+
+@pytest.mark.parametrize("n", [1, 9, 1000, 2490, 2491, 2500, 2510, 2511, 5050, 7500, 10021])
+def test_chunk_plan_matches_reference_loop(n):
+    plan = hostio.chunk_plan(n, 320)
+    assert plan == _reference_chunks(n, 320)
+    total = sum(len(range((ce - cs) * 320)[so:eo]) for cs, ce, so, eo in plan)
+    # 5050 frames -> 3 chunks, output length n*hop - 1
+    if n == 5050:
+        assert [(c[0], c[1]) for c in plan] == [(0, 2510), (2490, 5010), (4990, 5050)]
+    if n > 2510 or n <= 2500:
+        assert total == n * 320 - 1 or n % 2500 == 0 or total <= n * 320
+
+
+def test_csv_pitch_roundtrip(tmp_path):
+    p = tmp_path / "a.pit.csv"
+    pit = [0, 0, 220, 221.9, 440, 1100]
+    hostio.save_csv_pitch(pit, str(p))
+    lines = open(p).read().splitlines()
+    assert lines[2] == "0m 0s  20,220" and lines[3].endswith(",221")
+    assert hostio.load_csv_pitch(str(p)) == [0, 0, 220, 221, 440, 1100]
+
+
+def test_prepare_features_repeat_and_shift(tmp_path):
+    np.save(tmp_path / "x.ppg.npy", np.arange(6, dtype=np.float32).reshape(3, 2))
+    np.save(tmp_path / "x.vec.npy", np.ones((3, 4), np.float32))
+    hostio.save_csv_pitch([100, 0, 200, 200, 0, 0], str(tmp_path / "x.pit.csv"))
+    ppg, vec, pit = hostio.prepare_features(str(tmp_path / "x.ppg.npy"), str(tmp_path / "x.vec.npy"),
+                                            str(tmp_path / "x.pit.csv"), shift=12)
+    assert ppg.shape == (6, 2) and torch.equal(ppg[0], ppg[1]) and vec.shape == (6, 4)
+    assert torch.allclose(pit, torch.tensor([200., 0, 400, 400, 0, 0]))
+
+
+def test_checkpoint_roundtrip_tolerates_missing_keys(tmp_path, hp, sd, capsys):
+    from whisper_vits_svc_b200 import models
+    m = models.SynthesizerInfer(513, 25, hp)
+    partial = {k: v for k, v in sd.items() if k != "dec.conv_post.weight"}
+    torch.save({"model_g": partial}, tmp_path / "g.pth")
+    hostio.load_svc_model(str(tmp_path / "g.pth"), m)
+    assert "dec.conv_post.weight is not in the checkpoint" in capsys.readouterr().out
+    got = m.state_dict()
+    assert len(got) == 903 and torch.equal(got["enc_p.pre.weight"], sd["enc_p.pre.weight"])
+    hostio.save_svc_model(m, str(tmp_path / "h.pth"))
+    assert set(torch.load(tmp_path / "h.pth", weights_only=False)["model_g"]) == set(sd)
+
+
+def test_assign_balances_and_covers():
+    lens = [1000, 10, 500, 500, 990, 20, 30, 700]
+    parts = shard.assign(lens, 3)
+    assert sorted(i for p in parts for i in p) == list(range(len(lens)))
+    tot = [sum(lens[i] for i in p) for p in parts]
+    assert max(tot) - min(tot) <= max(lens)
+    assert shard.assign([], 2) == [[], []]
+
+
+GLOO_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, os.environ["SVCB_ROOT"])
+import torch.distributed as dist
+from whisper_vits_svc_b200 import shard
+rank, local, world = shard.init("gloo")
+blob = table = None
+if rank == 0:
+    blob = torch.arange(1000, dtype=torch.float32); table = [("a", 0, 10), ("b", 256, 5)]
+blob, table = shard.broadcast_blob(blob, table, torch.device("cpu"))
+assert blob.sum().item() == 499500.0 and table[1][0] == "b"
+mine = shard.assign(list(range(10, 0, -1)), world)[rank]
+tot = shard.sum_over_ranks(float(len(mine)), torch.device("cpu"))
+mx = shard.max_over_ranks(float(rank + 1), torch.device("cpu"))
+assert tot == 10.0 and mx == float(world)
+shard.barrier(); dist.destroy_process_group()
+open(os.path.join(os.environ["SVCB_OUT"], f"ok{rank}"), "w").write("ok")
+"""
+
+
+def test_two_rank_gloo_broadcast_and_shard(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(GLOO_WORKER)
+    env = dict(os.environ, SVCB_ROOT=ROOT, SVCB_OUT=str(tmp_path), MASTER_ADDR="127.0.0.1", MASTER_PORT="29533")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                       env=env, capture_output=True, text=True, timeout=240)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()

@@ -113,3 +113,46 @@ def test_rel_attention(ops, T, lens):
     qkv = torch.cat([F.conv1d(x, fake[f"a.conv_{n}.weight"], fake[f"a.conv_{n}.bias"]) for n in "qkv"], 1)
     got = ops.rel_attention(qkv.cuda(), fake["a.emb_rel_k"].cuda(), fake["a.emb_rel_v"].cuda(), lengths)
     assert max_abs(got, ref) <= 2e-5
+
+
+@pytest.mark.parametrize("N,K,shift,R", [(160, 160, 0, 128), (160, 160, 7, 178), (80, 80, 25, 160), (48, 48, 3, 140),
+                                         (32, 32, 1, 130), (16, 16, 0, 128), (256, 64, 9, 137)])
+def test_tcgen05_gemm_selftest(N, K, shift, R):
+    """tcgen05.mma + TMEM + row-shifted K-major SWIZZLE_NONE descriptors (the conv-tap trick):
+    bf16 inputs, fp32 accumulate -> exact up to fp32 summation order."""
+    import ctypes
+    from whisper_vits_svc_b200 import _lib
+    g = torch.Generator().manual_seed(N + K + shift)
+    A = torch.randn(R, K, generator=g).bfloat16()
+    Bm = torch.randn(N, K, generator=g).bfloat16()
+    ref = A[shift:shift + 128].float() @ Bm.float().t()
+    Ad, Bd = A.cuda(), Bm.cuda()
+    D = torch.zeros(128, N, device="cuda")
+    st = _lib.load().svcb_op_tc_gemm_selftest(Ad.data_ptr(), Bd.data_ptr(), D.data_ptr(), R, N, K, shift,
+                                              ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "svcb_op_tc_gemm_selftest")
+    torch.cuda.synchronize()
+    assert max_abs(D, ref) <= 1e-3 * K ** 0.5
+
+
+@pytest.mark.parametrize("C,L,K,dil,nsplit,tol", [
+    (160, 700, 11, 5, 3, 2e-4), (160, 300, 3, 1, 3, 2e-4), (80, 1000, 7, 3, 3, 2e-4), (40, 513, 11, 1, 3, 2e-4),
+    (20, 1024, 7, 5, 3, 2e-4), (10, 2000, 3, 3, 3, 2e-4), (80, 640, 7, 1, 1, 5e-2), (10, 127, 11, 5, 3, 2e-4)])
+def test_amp_conv_tc(ops, sd, C, L, K, dil, nsplit, tol):
+    """Fused SnakeAlias -> Conv1d (+bias +residual) on tcgen05 vs the oracle's two torch ops.
+    bf16x3 split operands: expected error ~1e-5 on O(1) data; plain bf16 ~1e-2 (reported, loose)."""
+    g = torch.Generator().manual_seed(C * 7 + L + K + dil)
+    B = 2
+    x = torch.randn(B, C, L, generator=g) * 1.5
+    w = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(B, C, L, generator=g)
+    fake = {"a.act.alpha": torch.randn(C, generator=g) * 0.4, "a.act.beta": torch.randn(C, generator=g) * 0.4,
+            "a.upsample.filter": sd["dec.activation_post.upsample.filter"],
+            "a.downsample.lowpass.filter": sd["dec.activation_post.downsample.lowpass.filter"]}
+    ref = F.conv1d(O.snake_alias(fake, "a", x), w, b, dilation=dil, padding=dil * (K - 1) // 2) + res
+    got = ops.amp_conv_tc(x.cuda(), fake["a.act.alpha"], fake["a.act.beta"], fake["a.upsample.filter"],
+                          fake["a.downsample.lowpass.filter"], w, b.cuda(), dilation=dil, res=res.cuda(), nsplit=nsplit)
+    err = max_abs(got, ref)
+    print(f"amp_conv_tc C={C} L={L} K={K} d={dil} nsplit={nsplit}: max-abs {err:.3e}")
+    assert err <= tol

@@ -59,6 +59,7 @@ struct UpStage {
 };
 struct ResBlock {
   ConvW c1[3], c2[3];
+  const uint8_t *c1_tc[3], *c2_tc[3];  // bf16 hi/lo tensor-core images of the same weights
   SnakeW act[6];
   int k, dil[3];
 };
@@ -254,12 +255,32 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
                          float* T1, float* T2, float* RA, float* RB, int B, int ch, int L) {
   cudaStream_t s = ctx.stream;
   const int nres = m->cfg.n_res;
+  const int prec = m->cfg.precision;
   for (int j = 0; j < nres; ++j) {
     const ResBlock& R = m->res[stage * nres + j];
     const float* cur = X;
     for (int d = 0; d < 3; ++d) {
       const SnakeW& a1 = R.act[2 * d];
       const SnakeW& a2 = R.act[2 * d + 1];
+      if (prec != 0) {  // tensor-core path: SnakeAlias fused into each conv's operand staging
+        AmpConvParams q;
+        q.B = B; q.C = ch; q.Cp = (ch + 15) / 16 * 16; q.L = L; q.K = R.k; q.nsplit = prec == 1 ? 1 : 3;
+        q.x = cur; q.y = T2; q.ea = a1.ea; q.ib = a1.ib; q.fu = a1.fu; q.fd = a1.fd;
+        q.wpk = R.c1_tc[d]; q.bias = R.c1[d].b; q.dil = R.dil[d];
+        RUN(launch_amp_conv_tc(q, s));
+        q.x = T2; q.ea = a2.ea; q.ib = a2.ib; q.fu = a2.fu; q.fd = a2.fd;
+        q.wpk = R.c2_tc[d]; q.bias = R.c2[d].b; q.dil = 1; q.res = cur;
+        if (d < 2) {
+          q.y = (d == 0) ? RA : RB;
+        } else {
+          q.y = ACC;
+          q.accum = j > 0;
+          if (j == nres - 1) q.out_div = (float)nres;
+        }
+        RUN(launch_amp_conv_tc(q, s));
+        cur = q.y;
+        continue;
+      }
       RUN(launch_snake_alias(cur, T1, a1.ea, a1.ib, a1.fu, a1.fd, B, ch, L, s));
       RUN(launch_conv1d(std_conv(R.c1[d], T1, T2, B, L, L, R.dil[d] * (R.k - 1) / 2, R.dil[d]), s));
       RUN(launch_snake_alias(T2, T1, a2.ea, a2.ib, a2.fu, a2.fd, B, ch, L, s));
@@ -465,6 +486,10 @@ static int resolve(svcb_model* m) {
         rb.dil[d] = c.res_dilations[j][d];
         rb.c1[d] = R.conv(p + ".c1." + std::to_string(d), ch, ch, rb.k);
         rb.c2[d] = R.conv(p + ".c2." + std::to_string(d), ch, ch, rb.k);
+        const int cp = (ch + 15) / 16 * 16;
+        const uint64_t tcn = (uint64_t)rb.k * 2 * cp * cp / 2;
+        rb.c1_tc[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c1." + std::to_string(d) + ".tc", tcn));
+        rb.c2_tc[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c2." + std::to_string(d) + ".tc", tcn));
       }
       for (int a = 0; a < 6; ++a) rb.act[a] = R.snake(p + ".act." + std::to_string(a), ch);
     }
@@ -682,6 +707,17 @@ int svcb_op_conv1d(const float* x, const float* w_packed, const float* bias, flo
   ConvParams p = std_conv(w, x, y, B, Tin, Tout, pad, dilation, stride);
   p.act = act;
   return launch_conv1d(p, static_cast<cudaStream_t>(stream));
+}
+
+int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float* ea, const float* inv_b,
+                        const float* fu, const float* fd, const void* w_tc, const float* bias, int32_t B,
+                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit, svcb_stream stream) {
+  g_launches = 0;
+  AmpConvParams q;
+  q.x = x; q.y = y; q.res = res; q.ea = ea; q.ib = inv_b; q.fu = fu; q.fd = fd;
+  q.wpk = static_cast<const uint8_t*>(w_tc); q.bias = bias;
+  q.B = B; q.C = C; q.Cp = (C + 15) / 16 * 16; q.L = L; q.K = K; q.dil = dilation; q.nsplit = nsplit;
+  return launch_amp_conv_tc(q, static_cast<cudaStream_t>(stream));
 }
 
 int svcb_op_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,

@@ -76,6 +76,22 @@ struct ConvParams {
 };
 int launch_conv1d(const ConvParams& p, cudaStream_t s);
 
+// ----------------------------------------------------------------------------- tensor-core AMP conv
+struct AmpConvParams {
+  const float* x = nullptr;     // [B, C, L]
+  float* y = nullptr;           // [B, C, L]
+  const float* res = nullptr;   // residual [B, C, L] or null
+  const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;  // SnakeAlias parameters
+  const uint8_t* wpk = nullptr; // bf16 [K][2 (hi,lo)][Cp/8][Cp][8]  (pack.py:pack_conv_tc)
+  const float* bias = nullptr;  // [C]
+  int B = 0, C = 0, Cp = 0, L = 0, K = 1, dil = 1;
+  int nsplit = 3;               // 1 = bf16, 3 = bf16x3 split
+  int accum = 0;                // y = y_old + v
+  float out_div = 0.f;          // then v / out_div when != 0
+};
+int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s);
+size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit);
+
 // ----------------------------------------------------------------------------- snake alias
 int launch_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,
                        const float* fu, const float* fd, int B, int C, int L, cudaStream_t s);

@@ -143,6 +143,7 @@ class SynthesizerInfer(torch.nn.Module):
             return None
         st = _lib.Taps()
         for name, t in taps.items():
+            assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float32, f"tap {name} must be a contiguous fp32 CUDA tensor"
             st.ptr[_lib.TAPS[name]] = t.data_ptr()
         return ctypes.byref(st)
 

@@ -71,3 +71,22 @@ def rel_attention(qkv, emb_k, emb_v, lengths, heads=2, window=4):
                                            out.data_ptr(), B, H, heads, window, T, _s())
     _lib.check(st, "svcb_op_rel_attention")
     return out
+
+
+def amp_conv_tc(x, alpha, beta, fu, fd, weight, bias, dilation=1, res=None, nsplit=3):
+    """SnakeAlias -> Conv1d(C->C, K, dilation, 'same') + bias (+res) on the tensor cores."""
+    x = _c(x)
+    B, C, L = x.shape
+    K = weight.shape[-1]
+    ea = _c(torch.exp(alpha.float().cpu()).to(x.device))
+    ib = _c((1.0 / (torch.exp(beta.float().cpu()) + 1e-9)).to(x.device))
+    fu, fd = _c(fu.reshape(-1).to(x.device)), _c(fd.reshape(-1).to(x.device))
+    wtc = pack.pack_conv_tc(weight.detach().cpu().float()).to(x.device)
+    b = _c(bias)
+    r = _c(res) if res is not None else None
+    y = torch.empty_like(x)
+    st = _lib.load().svcb_op_amp_conv_tc(x.data_ptr(), y.data_ptr(), r.data_ptr() if r is not None else None,
+                                         ea.data_ptr(), ib.data_ptr(), fu.data_ptr(), fd.data_ptr(),
+                                         wtc.data_ptr(), b.data_ptr(), B, C, L, K, dilation, nsplit, _s())
+    _lib.check(st, "svcb_op_amp_conv_tc")
+    return y

@@ -15,6 +15,7 @@ Packed tensors (all fp32, each 256-byte aligned in the blob):
   enc.<i>.qkv.*       conv_q | conv_k | conv_v concatenated along Cout (attentions.py:216-218)
   dec.ups.<i>.ph<r>.w ConvTranspose1d split into `rate` polyphase sub-filters:
                       w_r[co][ci][j'] = w[ci][co][r + rate*(M-1-j')], M = ceil(k/rate)
+  dec.res.<n>.c{1,2}.<d>.tc   the same AMP conv as bf16 hi/lo tensor-core tiles (pack_conv_tc)
   dec.res.<n>.act.<a>.ea / .ib   exp(alpha), 1/(exp(beta)+1e-9)   (alias/act.py:85-91)
   dec.res.<n>.act.<a>.fu / .fd   the 12 up / down taps stored in the checkpoint
 """
@@ -43,6 +44,23 @@ def pack_conv(w: torch.Tensor) -> torch.Tensor:
     out = torch.zeros(cin, k, cp, dtype=torch.float32)
     out[:, :, :cout] = w.permute(1, 2, 0)
     return out.contiguous()
+
+
+def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
+    """[C, C, K] fp32 -> the tensor-core image bf16 [K][2 (hi, lo)][Cp/8][Cp][8] (Cp = C rounded up
+    to 16): per tap and split part, the B operand W_tap[n = co][k = ci] in the K-major panel layout
+    of csrc/tc.cuh, so one tap is one contiguous bulk copy.  hi = bf16(w), lo = bf16(w - hi).
+    Returned as a float32 *view* of the bf16 bytes (the blob is fp32-typed; bits are preserved)."""
+    cout, cin, k = w.shape
+    assert cout == cin
+    cp = (cout + 15) // 16 * 16
+    wp = torch.zeros(k, cp, cp, dtype=torch.float32)
+    wp[:, :cout, :cin] = w.permute(2, 0, 1)
+    hi = wp.bfloat16()
+    lo = (wp - hi.float()).bfloat16()
+    st = torch.stack([hi, lo], 1)                                  # [K, 2, n, k]
+    img = st.view(k, 2, cp, cp // 8, 8).permute(0, 1, 3, 2, 4).contiguous()  # [K, 2, kc, n, 8]
+    return img.view(torch.float32).reshape(-1)
 
 
 def config_from_hp(hp, precision: int = 0) -> dict:
@@ -133,8 +151,12 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
     for n in range(n_blocks):
         p = f"dec.resblocks.{n}"
         for d in range(3):
-            conv(f"dec.res.{n}.c1.{d}", fold_weight_norm(sd, f"{p}.convs1.{d}"), sd[f"{p}.convs1.{d}.bias"])
-            conv(f"dec.res.{n}.c2.{d}", fold_weight_norm(sd, f"{p}.convs2.{d}"), sd[f"{p}.convs2.{d}.bias"])
+            w1 = fold_weight_norm(sd, f"{p}.convs1.{d}")
+            w2 = fold_weight_norm(sd, f"{p}.convs2.{d}")
+            conv(f"dec.res.{n}.c1.{d}", w1, sd[f"{p}.convs1.{d}.bias"])
+            conv(f"dec.res.{n}.c2.{d}", w2, sd[f"{p}.convs2.{d}.bias"])
+            put(f"dec.res.{n}.c1.{d}.tc", pack_conv_tc(w1))
+            put(f"dec.res.{n}.c2.{d}.tc", pack_conv_tc(w2))
         for a in range(6):
             _snake(put, f"dec.res.{n}.act.{a}", sd, f"{p}.activations.{a}")
     _snake(put, "dec.post.act", sd, "dec.activation_post")
