@@ -144,6 +144,35 @@ int svcb_infer(const svcb_model* m, const float* ppg, const float* vec, const fl
 /* Number of kernels enqueued by the most recent call on this thread (bench.py's gpu_launches). */
 int64_t svcb_last_launch_count(void);
 
+/* ------------------------------------------------------------------ PPG extractor (Whisper) */
+/* ModelDimensions of the checkpoint (whisper/model.py:14-25) after the loader's truncation
+ * (whisper/inference.py:16-19): n_layer = kept blocks = n_audio_layer - n_audio_layer/4. */
+typedef struct {
+  int32_t n_mels, n_ctx, n_state, n_head, n_layer;
+} svcb_whisper_config;
+typedef struct svcb_whisper svcb_whisper;
+
+/* Replaces whisper.inference.load_model (whisper/inference.py:11-29).  Blob names/layouts:
+ * whisper-vits-svc_b200/whisper_infer.py:pack_whisper (linear weights bf16, the rest fp32). */
+int svcb_whisper_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host,
+                        int32_t n_entries, const svcb_whisper_config* cfg_host, svcb_whisper** out);
+void svcb_whisper_destroy(svcb_whisper* w);
+size_t svcb_whisper_workspace_bytes(const svcb_whisper* w, int32_t B, int32_t n_frames);
+/* Replaces AudioEncoder.forward (whisper/model.py:144-163): mel [B, n_mels, n_frames] fp32 ->
+ * out [B, (n_frames-1)/2+1, n_state] fp32.  bf16 tensor-core GEMMs/attention, fp32 accumulate,
+ * fp32 residual stream (the reference itself runs fp16 on GPU, whisper/inference.py:22-23). */
+int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int32_t B, int32_t n_frames,
+                        void* ws, size_t ws_bytes, svcb_stream stream);
+
+/* Operator entry points of the encoder (unit tests):
+ * out[M,N] = A[M,K] . W[N,K]^T + bias with epilogue 0: bf16 out, 1: GELU(erf) then bf16 out,
+ * 2: + res (fp32 [M,N]) -> fp32 out.  A, W bf16 row-major; N % 128 == 0, K % 64 == 0. */
+int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
+                      int32_t M, int32_t N, int32_t K, int32_t epilogue, svcb_stream stream);
+/* softmax(q k^T / sqrt(64)) v per head: qkv bf16 [B*T, 3*D] rows (q|k|v), out bf16 [B*T, D]. */
+int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
+                           svcb_stream stream);
+
 /* Per-kernel timing for roofline reports: after svcb_timing_enable(1) every launch is bracketed
  * by CUDA events on its stream; after the caller synchronises, svcb_timing_report() returns
  * "name launches total_ms algorithmic_flops algorithmic_bytes" lines.  Not thread-safe; off by

@@ -1,0 +1,76 @@
+"""GPU parity of the PPG extractor (truncated Whisper encoder) against the oracle.
+The encoder computes GEMMs/attention with bf16 operands (fp32 accumulate); the reference itself
+runs fp16 on GPU (whisper/inference.py:22-23), so the gate is relative: rel-L2 <= 2e-2 and
+cosine >= 0.999 against the fp32 oracle (SURVEY.md §8c tolerance plan)."""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import whisper_oracle as W
+from tests.util import max_abs, rel_l2
+from whisper_vits_svc_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (300, 256, 128, 0), (1000, 384, 1280, 1), (257, 1280, 320, 2),
+                                       (3000, 3840, 1280, 0)])
+def test_gemm_bf16(M, N, K, epi):
+    from whisper_vits_svc_b200 import _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    A = (torch.randn(M, K, generator=g)).bfloat16()
+    Wt = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
+    bias = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    ref = A.float() @ Wt.float().t() + bias
+    if epi == 1:
+        ref = F.gelu(ref)
+    if epi == 2:
+        ref = ref + res
+    Ad, Wd, bd, rd = A.cuda(), Wt.cuda(), bias.cuda(), res.cuda()
+    out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 2 else torch.bfloat16)
+    st = _lib.load().svcb_op_gemm_bf16(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                                       rd.data_ptr() if epi == 2 else None, M, N, K, epi, _s())
+    _lib.check(st, "svcb_op_gemm_bf16")
+    torch.cuda.synchronize()
+    tol = 2e-4 * K ** 0.5 if epi == 2 else 3e-2   # bf16 output rounding dominates for epi 0/1
+    assert max_abs(out.float(), ref) <= tol
+
+
+@pytest.mark.parametrize("B,T,heads", [(2, 100, 2), (1, 64, 4), (2, 1500, 2), (1, 333, 20)])
+def test_attention_bf16(B, T, heads):
+    from whisper_vits_svc_b200 import _lib
+    D = heads * 64
+    g = torch.Generator().manual_seed(T + heads)
+    qkv = torch.randn(B, T, 3 * D, generator=g).bfloat16()
+    q, k, v = [t.float().view(B, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(D, dim=-1)]
+    ref = (F.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, T, D)
+    qd = qkv.cuda()
+    out = torch.zeros(B, T, D, device="cuda", dtype=torch.bfloat16)
+    st = _lib.load().svcb_op_attention_bf16(qd.data_ptr(), out.data_ptr(), B, T, D, heads, _s())
+    _lib.check(st, "svcb_op_attention_bf16")
+    torch.cuda.synchronize()
+    assert max_abs(out.float(), ref) <= 2e-2
+
+
+@pytest.mark.parametrize("state,heads,layers,B,n", [(128, 2, 4, 2, 200), (256, 4, 4, 1, 301), (1280, 20, 4, 1, 400)])
+def test_encoder_vs_oracle(state, heads, layers, B, n):
+    from whisper_vits_svc_b200 import whisper_infer
+    dims = dict(synth.WHISPER_LARGE_V2_DIMS, n_audio_state=state, n_audio_head=heads, n_audio_layer=layers)
+    ck = synth.whisper_checkpoint(dims, seed=state)
+    g = torch.Generator().manual_seed(n)
+    mel = torch.randn(B, 80, n, generator=g).clamp(-1, 1.5)
+    ref = W.audio_encoder(ck, mel)
+    enc = whisper_infer.WhisperB200(ck, "cuda").encoder
+    got = enc(mel).cpu()
+    assert got.shape == ref.shape
+    r = rel_l2(got, ref)
+    cos = float(F.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    print(f"whisper D={state} layers={W.kept_layers(dims)}: rel-l2 {r:.3e}, cosine {cos:.6f}, max-abs {max_abs(got, ref):.3e}")
+    assert r <= 2e-2 and cos >= 0.999

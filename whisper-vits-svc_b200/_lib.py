@@ -56,6 +56,11 @@ class Config(ctypes.Structure):
         return c
 
 
+class WhisperConfig(ctypes.Structure):
+    _fields_ = [("n_mels", c_int32), ("n_ctx", c_int32), ("n_state", c_int32), ("n_head", c_int32),
+                ("n_layer", c_int32)]
+
+
 class TensorEntry(ctypes.Structure):
     _fields_ = [("name", c_char * 96), ("offset_bytes", c_uint64), ("numel", c_uint64)]
 
@@ -70,6 +75,12 @@ SIGNATURES = {
     "svcb_version": (c_int, []),
     "svcb_sizeof": (c_size_t, [c_int32]),
     "svcb_last_launch_count": (c_int64, []),
+    "svcb_whisper_create": (c_int, [c_void_p, c_size_t, POINTER(TensorEntry), c_int32, POINTER(WhisperConfig), POINTER(c_void_p)]),
+    "svcb_whisper_destroy": (None, [c_void_p]),
+    "svcb_whisper_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "svcb_whisper_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "svcb_op_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p]),
+    "svcb_op_attention_bf16": (c_int, [c_void_p, c_void_p] + [c_int32] * 4 + [c_void_p]),
     "svcb_timing_enable": (None, [c_int32]),
     "svcb_timing_report": (c_char_p, []),
     "svcb_model_create": (c_int, [c_void_p, c_size_t, POINTER(TensorEntry), c_int32, POINTER(Config), POINTER(c_void_p)]),

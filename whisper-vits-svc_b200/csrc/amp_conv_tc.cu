@@ -225,12 +225,12 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
     return SVCB_E_BAD_SHAPE;
   }
   const size_t smem = amp_conv_tc_smem_bytes(p.Cp, p.K, p.dil, p.nsplit);
-  if (smem > 227 * 1024) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
-  static bool attr = false;
-  if (!attr) {
+  if (smem > 227 * 1024 - 512) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
+  static size_t attr_bytes = 0;  // dynamic limit excludes the kernel's (small) static shared memory
+  if (smem > attr_bytes) {
     SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         227 * 1024));
-    attr = true;
+                                         (int)smem));
+    attr_bytes = smem;
   }
   dim3 grid((p.L + TC_M - 1) / TC_M, p.B);
   const double macs = (double)p.B * p.L * p.C * p.C * p.K;

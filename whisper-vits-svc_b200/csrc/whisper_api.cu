@@ -1,0 +1,174 @@
+// C ABI for the PPG extractor: truncated Whisper AudioEncoder (whisper/model.py:132-163 after the
+// loader's surgery, whisper/inference.py:11-29).  Stage pipeline:
+//   conv1+GELU -> conv2(stride 2)+GELU+pos-emb -> n_layer x { LN -> QKV GEMM -> flash attention ->
+//   out-proj GEMM (+residual) -> LN -> MLP GEMM+GELU -> MLP GEMM (+residual) } -> ln_post
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace svcb {
+int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
+                   int M, int N, int K, int epi, cudaStream_t s);
+int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, cudaStream_t s);
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
+                   cudaStream_t s);
+struct WBlock {
+  const float *ln1g, *ln1b, *ln2g, *ln2b, *bqkv, *bo, *b1, *b2;
+  const void *wqkv, *wo, *w1, *w2;
+};
+}  // namespace svcb
+
+struct svcb_whisper {
+  svcb_whisper_config cfg;
+  std::map<std::string, std::pair<const float*, uint64_t>> tensors;
+  const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *pos, *lnp_g, *lnp_b;
+  std::vector<svcb::WBlock> blocks;
+};
+
+using namespace svcb;
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct WLayout {
+  size_t h1, x, a, qkv, att, mid, total;
+  int n2, M;
+};
+static WLayout whisper_layout(const svcb_whisper_config& c, int B, int n) {
+  WLayout L;
+  L.n2 = (n - 1) / 2 + 1;
+  L.M = B * L.n2;
+  const size_t D = c.n_state;
+  size_t off = 0;
+  L.h1 = off; off = align256(off + (size_t)B * D * n * 4);
+  L.x = off; off = align256(off + (size_t)L.M * D * 4);
+  L.a = off; off = align256(off + (size_t)L.M * D * 2);
+  L.qkv = off; off = align256(off + (size_t)L.M * 3 * D * 2);
+  L.att = off; off = align256(off + (size_t)L.M * D * 2);
+  L.mid = off; off = align256(off + (size_t)L.M * 4 * D * 2);
+  L.total = off + 4096;
+  return L;
+}
+
+extern "C" {
+
+int svcb_whisper_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host,
+                        int32_t n_entries, const svcb_whisper_config* cfg_host, svcb_whisper** out) {
+  if (!dev_blob || !table_host || !cfg_host || !out) { set_error("null argument"); return SVCB_E_BAD_SHAPE; }
+  if (((uintptr_t)dev_blob & 255) != 0) { set_error("weight blob must be 256-byte aligned"); return SVCB_E_BAD_ALIGN; }
+  const svcb_whisper_config& c = *cfg_host;
+  if (c.n_state % 128 || c.n_state / c.n_head != 64 || c.n_layer < 1 || c.n_state > 2048) {
+    set_error("whisper config: n_state must be a multiple of 128 (<= 2048) with 64-wide heads");
+    return SVCB_E_UNSUPPORTED;
+  }
+  int dev = 0;
+  SVCB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SVCB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) { set_error("libsvc_b200 is built for sm_100a only"); return SVCB_E_UNSUPPORTED; }
+  svcb_whisper* w = new svcb_whisper();
+  w->cfg = c;
+  const char* blob = static_cast<const char*>(dev_blob);
+  for (int i = 0; i < n_entries; ++i) {
+    const svcb_tensor_entry& e = table_host[i];
+    if (e.offset_bytes % 256 != 0 || e.offset_bytes + e.numel * sizeof(float) > blob_bytes) {
+      set_error(std::string("bad table entry: ") + e.name);
+      delete w;
+      return SVCB_E_BAD_ALIGN;
+    }
+    w->tensors[std::string(e.name, strnlen(e.name, sizeof(e.name)))] = {
+        reinterpret_cast<const float*>(blob + e.offset_bytes), e.numel};
+  }
+  bool ok = true;
+  std::string missing;
+  auto get = [&](const std::string& n, uint64_t min_numel) -> const float* {
+    auto it = w->tensors.find(n);
+    if (it == w->tensors.end() || it->second.second < min_numel) { if (ok) missing = n; ok = false; return nullptr; }
+    return it->second.first;
+  };
+  const uint64_t D = c.n_state;
+  w->conv1_w = get("conv1.w", (uint64_t)c.n_mels * 3 * D); w->conv1_b = get("conv1.b", D);
+  w->conv2_w = get("conv2.w", D * 3 * D); w->conv2_b = get("conv2.b", D);
+  w->pos = get("pos", (uint64_t)c.n_ctx * D);
+  w->lnp_g = get("ln_post.g", D); w->lnp_b = get("ln_post.b", D);
+  w->blocks.resize(c.n_layer);
+  for (int i = 0; i < c.n_layer; ++i) {
+    const std::string p = "blk." + std::to_string(i);
+    WBlock& b = w->blocks[i];
+    b.ln1g = get(p + ".ln1.g", D); b.ln1b = get(p + ".ln1.b", D);
+    b.ln2g = get(p + ".ln2.g", D); b.ln2b = get(p + ".ln2.b", D);
+    b.wqkv = get(p + ".wqkv", 3 * D * D / 2); b.bqkv = get(p + ".bqkv", 3 * D);
+    b.wo = get(p + ".wo", D * D / 2); b.bo = get(p + ".bo", D);
+    b.w1 = get(p + ".w1", 4 * D * D / 2); b.b1 = get(p + ".b1", 4 * D);
+    b.w2 = get(p + ".w2", 4 * D * D / 2); b.b2 = get(p + ".b2", D);
+  }
+  if (!ok) { set_error("tensor missing or too small in whisper blob: " + missing); delete w; return SVCB_E_MISSING_TENSOR; }
+  *out = w;
+  return SVCB_OK;
+}
+
+void svcb_whisper_destroy(svcb_whisper* w) { delete w; }
+
+size_t svcb_whisper_workspace_bytes(const svcb_whisper* w, int32_t B, int32_t n_frames) {
+  if (!w || B <= 0 || n_frames <= 0) return 0;
+  return whisper_layout(w->cfg, B, n_frames).total;
+}
+
+int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int32_t B, int32_t n_frames,
+                        void* ws, size_t ws_bytes, svcb_stream stream) {
+  if (!w || !mel || !out || B <= 0 || n_frames <= 0) { set_error("svcb_whisper_encode: bad argument"); return SVCB_E_BAD_SHAPE; }
+  const svcb_whisper_config& c = w->cfg;
+  const WLayout L = whisper_layout(c, B, n_frames);
+  if (L.n2 > c.n_ctx) { set_error("incorrect audio shape: more than n_audio_ctx positions"); return SVCB_E_BAD_SHAPE; }
+  if (!ws || ((uintptr_t)ws & 255) || ws_bytes < L.total) { set_error("whisper workspace too small or misaligned"); return SVCB_E_WORKSPACE; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* h1 = reinterpret_cast<float*>(base + L.h1);
+  float* x = reinterpret_cast<float*>(base + L.x);
+  void* a = base + L.a; void* qkv = base + L.qkv; void* att = base + L.att; void* mid = base + L.mid;
+  const int D = c.n_state, n = n_frames, n2 = L.n2, M = L.M;
+  {  // conv1 + GELU (whisper/model.py:149)
+    ConvParams p;
+    p.x = mel; p.sxb = (long long)c.n_mels * n; p.sxc = n; p.sxt = 1;
+    p.w = w->conv1_w; p.cout_pad = D; p.bias = w->conv1_b;
+    p.y = h1; p.syb = (long long)D * n; p.syc = n; p.syt = 1;
+    p.B = B; p.Cin = c.n_mels; p.Cout = D; p.Tin = n; p.K = 3; p.pad = 1; p.nq = n; p.act = ACT_GELU;
+    SVCB_TRY(launch_conv1d(p, s));
+  }
+  {  // conv2 stride 2 + GELU, permute to time-major, + positional embedding (:150-157)
+    ConvParams p;
+    p.x = h1; p.sxb = (long long)D * n; p.sxc = n; p.sxt = 1;
+    p.w = w->conv2_w; p.cout_pad = D; p.bias = w->conv2_b;
+    p.y = x; p.syb = (long long)n2 * D; p.syc = 1; p.syt = D;
+    p.B = B; p.Cin = D; p.Cout = D; p.Tin = n; p.K = 3; p.stride = 2; p.pad = 1; p.nq = n2; p.act = ACT_GELU;
+    p.addvec = w->pos;
+    SVCB_TRY(launch_conv1d(p, s));
+  }
+  for (int i = 0; i < c.n_layer; ++i) {
+    const WBlock& b = w->blocks[i];
+    SVCB_TRY(launch_ln_rows(x, b.ln1g, b.ln1b, a, M, D, true, s));
+    SVCB_TRY(launch_gemm_tc(a, b.wqkv, b.bqkv, qkv, nullptr, M, 3 * D, D, 0, s));
+    SVCB_TRY(launch_whisper_attention(qkv, att, B, n2, D, c.n_head, s));
+    SVCB_TRY(launch_gemm_tc(att, b.wo, b.bo, x, x, M, D, D, 2, s));
+    SVCB_TRY(launch_ln_rows(x, b.ln2g, b.ln2b, a, M, D, true, s));
+    SVCB_TRY(launch_gemm_tc(a, b.w1, b.b1, mid, nullptr, M, 4 * D, D, 1, s));
+    SVCB_TRY(launch_gemm_tc(mid, b.w2, b.b2, x, x, M, D, 4 * D, 2, s));
+  }
+  return launch_ln_rows(x, w->lnp_g, w->lnp_b, out, M, D, false, s);
+}
+
+
+int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
+                      int32_t M, int32_t N, int32_t K, int32_t epilogue, svcb_stream stream) {
+  return launch_gemm_tc(A_bf16, W_bf16, bias, out, res, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+}
+
+int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
+                           svcb_stream stream) {
+  return launch_whisper_attention(qkv_bf16, out_bf16, B, T, D, heads, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
