@@ -208,13 +208,23 @@ int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float*
                           const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
                           int32_t window, int32_t T, svcb_stream stream);
 
-/* One fused `SnakeAlias -> Conv1d(C->C, K, dilation, same padding) + bias (+ res)` link of
- * AMPBlock.forward (vits_decoder/bigv.py:50-58) on the tensor cores.  w_tc = pack.py:pack_conv_tc
- * image; nsplit 1 = bf16, 3 = bf16x3 (parity grade). */
+/* General stride-1 "same" Conv1d on the tensor cores (csrc/conv_tc.cu): x [B,Cin,T] fp32,
+ * w_tc = pack.py:pack_conv_tc_general image, y [B,Cout,T] ([B,Cout/2,T] with the gate flag).
+ * flags: 1 input mask, 2 output mask (need lengths), 4 WaveNet gate on interleaved channel pairs,
+ * 8 accumulate into y.  act as svcb_op_conv1d.  nsplit 1 = bf16, 3 = bf16x3. */
+int svcb_op_conv_tc(const float* x, const void* w_tc, const float* bias, float* y, const float* res,
+                    const int64_t* lengths, int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t K,
+                    int32_t dilation, int32_t nsplit, int32_t flags, int32_t act, svcb_stream stream);
+
+/* One `SnakeAlias -> Conv1d(C->C, K, dilation, same padding) + bias (+ res)` link of
+ * AMPBlock.forward (vits_decoder/bigv.py:50-58) on the tensor cores: snake_pack (bf16 hi/lo operand
+ * image in `scratch`) followed by the tcgen05 convolution.  w_tc = pack.py:pack_conv_tc image;
+ * nsplit 1 = bf16, 3 = bf16x3 (parity grade). */
+size_t svcb_op_amp_conv_tc_scratch_bytes(int32_t B, int32_t C, int32_t L);
 int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float* ea, const float* inv_b,
                         const float* fu, const float* fd, const void* w_tc, const float* bias, int32_t B,
-                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit,
-                        svcb_stream stream);
+                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit, void* scratch,
+                        size_t scratch_bytes, svcb_stream stream);
 
 /* Self-test of the tcgen05/TMEM plumbing: D[128,N] = A[shift:shift+128, :K] . B[N,K]^T with
  * bf16 operands (row-major, device) and fp32 accumulation in tensor memory. */

@@ -156,3 +156,42 @@ def test_amp_conv_tc(ops, sd, C, L, K, dil, nsplit, tol):
     err = max_abs(got, ref)
     print(f"amp_conv_tc C={C} L={L} K={K} d={dil} nsplit={nsplit}: max-abs {err:.3e}")
     assert err <= tol
+
+
+@pytest.mark.parametrize("Cin,Cout,T,K,dil,nsplit,tol", [
+    (192, 384, 1000, 5, 1, 3, 2e-4), (192, 576, 300, 1, 1, 3, 2e-4), (640, 192, 257, 3, 1, 3, 2e-4),
+    (96, 192, 130, 1, 1, 3, 2e-4), (192, 640, 500, 3, 1, 3, 2e-4), (192, 320, 64, 7, 1, 3, 2e-4),
+    (1280, 192, 200, 5, 1, 3, 3e-4), (192, 96, 77, 1, 1, 1, 5e-2)])
+def test_conv_tc(ops, Cin, Cout, T, K, dil, nsplit, tol):
+    """General implicit-GEMM Conv1d on tcgen05 vs F.conv1d (fp32 CPU)."""
+    g = torch.Generator().manual_seed(Cin + Cout + T + K)
+    x = torch.randn(2, Cin, T, generator=g)
+    w = torch.randn(Cout, Cin, K, generator=g) / (Cin * K) ** 0.5
+    b = torch.randn(Cout, generator=g) * 0.1
+    ref = F.conv1d(x, w, b, dilation=dil, padding=dil * (K - 1) // 2)
+    got = ops.conv_tc(x.cuda(), w, b.cuda(), dilation=dil, nsplit=nsplit)
+    err = max_abs(got, ref)
+    print(f"conv_tc {Cin}->{Cout} T={T} K={K} nsplit={nsplit}: max-abs {err:.3e}")
+    assert err <= tol
+
+
+def test_conv_tc_epilogues(ops):
+    """masks, gate on interleaved pairs, residual, ReLU — the flags the prior/flow pipelines use."""
+    g = torch.Generator().manual_seed(99)
+    B, C, T = 2, 192, 150
+    x = torch.randn(B, C, T, generator=g)
+    lengths = torch.tensor([150, 101])
+    mask = O.sequence_mask(lengths, T).unsqueeze(1).float()
+    w = torch.randn(2 * C, C, 5, generator=g) / (C * 5) ** 0.5
+    b = torch.randn(2 * C, generator=g) * 0.1
+    a = F.conv1d(x, w, b, padding=2)
+    ref = torch.tanh(a[:, :C]) * torch.sigmoid(a[:, C:])
+    idx = torch.stack([torch.arange(C), torch.arange(C) + C], 1).reshape(-1)
+    got = ops.conv_tc(x.cuda(), w[idx], b[idx].cuda(), flags=4)
+    assert max_abs(got, ref) <= 2e-4
+    w2 = torch.randn(C, C, 3, generator=g) / (C * 3) ** 0.5
+    b2 = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(B, C, T, generator=g)
+    ref2 = torch.relu(F.conv1d(x * mask, w2, b2, padding=1)) * mask + res
+    got2 = ops.conv_tc(x.cuda(), w2, b2.cuda(), res=res.cuda(), lengths=lengths, flags=1 | 2, act=1)
+    assert max_abs(got2, ref2) <= 2e-4

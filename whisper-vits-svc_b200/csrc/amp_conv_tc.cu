@@ -1,107 +1,76 @@
-// AMP-block convolution on the 5th-gen tensor cores (tcgen05 + TMEM), with the anti-aliased
-// Snake activation fused as the operand-staging prologue and bias / residual / stage-mean fused
-// as the TMEM epilogue.
+// AMP-block link on the 5th-gen tensor cores, as two kernels that each stream at their own roofline:
 //
-// Replaces, per launch, one `SnakeAlias -> Conv1d(+bias) [-> + residual]` link of
-// AMPBlock.forward (vits_decoder/bigv.py:50-58; SnakeAlias = alias/act.py:124-128): 2 of the
-// ~10 kernels the CUDA-core path needs per link, and the only part of the generator whose
-// arithmetic is a dense contraction.
+//   snake_pack   SnakeAlias(x) -> bf16 hi/lo operand image in HBM            (CUDA cores, HBM-bound)
+//   amp_conv_tc  Conv1d(C->C, K, dilation) + bias (+residual, stage mean)    (tcgen05 + TMEM)
 //
-// Implicit GEMM, one CTA per (128 output samples, item):
-//   D[t, co] = sum_tap sum_ci A[t + tap*dil, ci] * W_tap[co, ci]        M=128, N=Cp, K=Cp per tap
-// * A (activations after SnakeAlias, zero outside the sequence = the conv's zero padding) is
-//   produced by the CUDA cores straight into shared memory in the K-major "panel" layout of
-//   tc.cuh, R = 128 + (K-1)*dil rows, so every tap is the SAME tile addressed with a descriptor
-//   advanced by tap*dil rows — no im2col, no re-staging.
-// * W_tap tiles (pre-packed by the host in the exact shared-memory image) stream through a
-//   2-stage ring with 1-D bulk copies (TMA engine) signalled on mbarriers.
-// * One thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32 in TMEM); tcgen05.commit frees
-//   ring slots and finally signals the epilogue warps, which read TMEM with tcgen05.ld.
-// * Precision: nsplit=1 plain bf16; nsplit=3 "bf16x3": A = Ah+Al, W = Wh+Wl (bf16 each) and
-//   D = Ah*Wh + Al*Wh + Ah*Wl, i.e. ~16 mantissa bits per operand — the parity-grade mode
-//   (measured waveform error 3e-5 vs 1.2e-2 for plain bf16).
+// Together they replace one `SnakeAlias -> Conv1d [-> + x]` link of AMPBlock.forward
+// (vits_decoder/bigv.py:50-58; SnakeAlias = vits_decoder/alias/act.py:124-128), SURVEY.md §8a rows
+// a9/a10.  A first version fused both into one CTA-per-tile kernel; measured on B200 it ran at the
+// CUDA-core path's speed (15 TFLOP/s) because the per-tile Snake prologue (20 x load->sync->FIR->
+// sync->FIR->sync with one resident CTA) was latency-bound and left the tensor pipe idle
+// (profiles/r01_notes.md).  Splitting lets the Snake pass run with 32 warps/SM and lets the conv
+// kernel feed its A operand with bulk (TMA-engine) copies.
+//
+// Operand image ("P8" layout): hi/lo bf16 [B][Cp/8][Lp][8], Lp = 32 + roundup(L,128) + 32, row =
+// 32 + t; rows outside the sequence and channels >= C are zero.  One (octet, row-range) of the A
+// tile is therefore ONE contiguous run of R*16 bytes = one bulk copy straight into the K-major
+// panel layout of tc.cuh, the zero rows are the conv's zero padding, and every tap is the same
+// tile addressed through a row-shifted descriptor.
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace svcb {
 
 constexpr int TC_M = 128;
-constexpr int TC_THREADS = 256;
+constexpr int P8_PAD = 32;
+
+__host__ __device__ inline int p8_rows_of(int L) { return P8_PAD + (L + 127) / 128 * 128 + P8_PAD; }
+int p8_rows(int L) { return p8_rows_of(L); }
 
 __device__ __forceinline__ float fast_sin(float x) {
-  // Cody-Waite reduction to [-pi, pi] then the SFU sine: abs error < 1e-6 for |x| < 1e3, an
-  // order of magnitude below the bf16x3 operand rounding this kernel already accepts.
+  // Cody-Waite reduction to [-pi, pi] then the SFU sine: abs error < 1e-6 for |x| < 1e3, an order
+  // of magnitude below the bf16x3 operand rounding already accepted here.
   const float k = rintf(x * 0.15915494309189535f);
   x = fmaf(k, -6.2831854820251465f, x);
   x = fmaf(k, 1.7484555e-7f, x);
   return __sinf(x);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
-amp_conv_tc_kernel(const AmpConvParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[2], bar_empty[2], bar_acc;
-  __shared__ uint32_t tmem_slot;
+// ------------------------------------------------------------------------------------ snake_pack
+constexpr int SP_TL = 512;  // image rows per CTA
+
+__global__ void __launch_bounds__(256)
+snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                  const float* __restrict__ ea, const float* __restrict__ inv_b,
+                  const float* __restrict__ fu, const float* __restrict__ fd, int C, int L, int Lp) {
+  extern __shared__ __align__(16) float sp_smem[];
+  constexpr int XW = SP_TL + 12, VW = 2 * SP_TL + 12;
+  float* xs = sp_smem;            // [8][XW]
+  float* vs = sp_smem + 8 * XW;   // [8][VW]
   __shared__ float f_up[12], f_dn[12];
-
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * TC_M;
-  const int P = p.dil * (p.K - 1) / 2;
-  const int R = TC_M + (p.K - 1) * p.dil;
-  const int KC = p.Cp / 8;
-  const int n0 = t0 - P;  // sequence position of A row 0
-  const uint32_t a_bytes = (uint32_t)KC * R * 16u;
-  const uint32_t wb = (uint32_t)p.Cp * p.Cp * 2u;
-  const int parts_w = p.nsplit == 3 ? 2 : 1;
-  const int nch = p.K * parts_w;
-  uint8_t* A_hi = smem;
-  uint8_t* A_lo = smem + a_bytes;  // only when nsplit == 3
-  uint8_t* W0 = smem + (p.nsplit == 3 ? 2u : 1u) * a_bytes;
-  uint8_t* W1 = W0 + wb;           // also the prologue's staging area
-  float* xs = reinterpret_cast<float*>(W1);        // [8][R + 12]
-  float* vs = xs + 8 * (R + 12);                   // [8][2R + 12]
-  const int XW = R + 12, VW = 2 * R + 12;
-
-  if (tid == 0) {
-    tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
-    tc::mbar_init(&bar_empty[0], 1); tc::mbar_init(&bar_empty[1], 1);
-    tc::mbar_init(&bar_acc, 1);
-    tc::fence_barrier_init();
-  }
-  if (tid < 12) { f_up[tid] = __ldg(p.fu + tid); f_dn[tid] = __ldg(p.fd + tid); }
-  const uint32_t ncols = tc::tmem_cols_for(p.Cp);
-  __syncwarp();
-  if (warp == 0) tc::tmem_alloc(&tmem_slot, ncols);
-  tc::fence_before_sync();
-  __syncthreads();
-  tc::fence_after_sync();
-  const uint32_t tmem = tmem_slot;
-
-  // first weight tile travels while the CUDA cores build A
-  if (tid == 128) {
-    tc::mbar_arrive_expect_tx(&bar_full[0], wb);
-    tc::bulk_g2s(W0, p.wpk, wb, &bar_full[0]);
-  }
-
-  // ------------------------------------------------------------------ prologue: A = SnakeAlias(x)
-  const float* xb = p.x + (long long)b * p.C * p.L;
-  for (int kc = 0; kc < KC; ++kc) {
-    // (a) raw x, 8 channels x (R+12) samples, replicate-clamped at the sequence ends
-    for (int idx = tid; idx < 8 * XW; idx += TC_THREADS) {
+  const int tid = threadIdx.x;
+  const int oc = blockIdx.y, b = blockIdx.z;
+  const int row0 = blockIdx.x * SP_TL;      // first image row of this CTA
+  const int n0 = row0 - P8_PAD;             // its sequence position
+  if (tid < 12) { f_up[tid] = __ldg(fu + tid); f_dn[tid] = __ldg(fd + tid); }
+  const long long img = ((long long)b * gridDim.y + oc) * Lp;
+  const bool any = n0 < L && n0 + SP_TL > 0 && oc * 8 < C;  // block-uniform
+  if (any) {
+    const float* xb = x + (long long)b * C * L;
+    for (int idx = tid; idx < 8 * XW; idx += 256) {
       const int c = idx / XW, i = idx - c * XW;
-      const int cg = kc * 8 + c;
+      const int cg = oc * 8 + c;
       int g = n0 - 6 + i;
-      g = min(max(g, 0), p.L - 1);
-      xs[idx] = cg < p.C ? __ldg(xb + (long long)cg * p.L + g) : 0.f;
+      g = min(max(g, 0), L - 1);
+      xs[idx] = cg < C ? __ldg(xb + (long long)cg * L + g) : 0.f;
     }
     __syncthreads();
-    // (b) 2x up-sampled Snake: v[m], m = 2*n0 - 5 + idx
-    for (int idx = tid; idx < 8 * (2 * R + 10); idx += TC_THREADS) {
-      const int c = idx / (2 * R + 10), iv = idx - c * (2 * R + 10);
-      const int cg = min(kc * 8 + c, p.C - 1);
+    constexpr int NV = 2 * SP_TL + 10;
+    for (int idx = tid; idx < 8 * NV; idx += 256) {
+      const int c = idx / NV, iv = idx - c * NV;
+      const int cg = min(oc * 8 + c, C - 1);
       int m = 2 * n0 - 5 + iv;
-      m = min(max(m, 0), 2 * p.L - 1);
+      m = min(max(m, 0), 2 * L - 1);
       const int a = m >> 1;
       const float* xp = xs + c * XW + (a - (n0 - 6));
       float acc = 0.f;
@@ -113,59 +82,130 @@ amp_conv_tc_kernel(const AmpConvParams p) {
         for (int d = -2; d <= 3; ++d) acc = fmaf(xp[d], f_up[6 - 2 * d], acc);
       }
       const float u = 2.f * acc;
-      const float sn = fast_sin(u * __ldg(p.ea + cg));
-      vs[c * VW + iv] = u + __ldg(p.ib + cg) * (sn * sn);
-    }
-    __syncthreads();
-    // (c) 12-tap decimation, bf16 split, one 16-byte K-chunk per row
-    for (int r = tid; r < R; r += TC_THREADS) {
-      const int tau = n0 + r;
-      const bool inside = tau >= 0 && tau < p.L;
-      __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float o = 0.f;
-        if (inside && kc * 8 + c < p.C) {
-          const float* vp = vs + c * VW + 2 * r;
-#pragma unroll
-          for (int k = 0; k < 12; ++k) o = fmaf(vp[k], f_dn[k], o);
-        }
-        hi[c] = __float2bfloat16_rn(o);
-        lo[c] = __float2bfloat16_rn(o - __bfloat162float(hi[c]));
-      }
-      *reinterpret_cast<uint4*>(A_hi + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(hi);
-      if (p.nsplit == 3)
-        *reinterpret_cast<uint4*>(A_lo + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(lo);
+      const float sn = fast_sin(u * __ldg(ea + cg));
+      vs[c * VW + iv] = u + __ldg(inv_b + cg) * (sn * sn);
     }
     __syncthreads();
   }
-  tc::fence_proxy_async_smem();  // generic-proxy writes of A -> visible to the tensor core (async proxy)
-  __syncthreads();
+  for (int r = tid; r < SP_TL; r += 256) {
+    const int row = row0 + r;
+    if (row >= Lp) break;
+    const int tau = n0 + r;
+    __align__(16) __nv_bfloat16 h8[8], l8[8];
+    const bool inside = any && tau >= 0 && tau < L;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      float o = 0.f;
+      if (inside && oc * 8 + c < C) {
+        const float2* vp = reinterpret_cast<const float2*>(vs + c * VW + 2 * r);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) {
+          const float2 v2 = vp[k];
+          o = fmaf(v2.x, f_dn[2 * k], o);
+          o = fmaf(v2.y, f_dn[2 * k + 1], o);
+        }
+      }
+      h8[c] = __float2bfloat16_rn(o);
+      l8[c] = __float2bfloat16_rn(o - __bfloat162float(h8[c]));
+    }
+    *reinterpret_cast<uint4*>(hi + (img + row) * 8) = *reinterpret_cast<const uint4*>(h8);
+    if (lo) *reinterpret_cast<uint4*>(lo + (img + row) * 8) = *reinterpret_cast<const uint4*>(l8);
+  }
+}
 
-  // ------------------------------------------------------------------ weight producer (1 thread)
+size_t p8_image_bytes(int B, int C, int L) {  // one of hi / lo
+  const int cp = (C + 15) / 16 * 16;
+  return (size_t)B * (cp / 8) * p8_rows_of(L) * 16;
+}
+
+int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
+                      const float* fd, int B, int C, int L, cudaStream_t s) {
+  if (B <= 0 || C <= 0 || L <= 0) return SVCB_OK;
+  const int cp = (C + 15) / 16 * 16, Lp = p8_rows_of(L);
+  const size_t smem = (size_t)(8 * (SP_TL + 12) + 8 * (2 * SP_TL + 12)) * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(snake_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  dim3 grid((Lp + SP_TL - 1) / SP_TL, cp / 8, B);
+  KernelScope ks("snake_pack", s, 70.0 * B * C * (double)L, (lo ? 8.0 : 6.0) * B * C * (double)L);
+  snake_pack_kernel<<<grid, 256, smem, s>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ea,
+                                            inv_b, fu, fd, C, L, Lp);
+  SVCB_LAUNCH_CHECK("snake_pack");
+  return SVCB_OK;
+}
+
+// ------------------------------------------------------------------------------------ amp_conv_tc
+__global__ void __launch_bounds__(192, 1)
+amp_conv_tc_kernel(const AmpConvParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_a, bar_full[2], bar_empty[2], bar_acc;
+  __shared__ uint32_t tmem_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TC_M;
+  const int P = p.dil * (p.K - 1) / 2;
+  const int R = TC_M + (p.K - 1) * p.dil;
+  const int KC = p.Cp / 8;
+  const uint32_t a_bytes = (uint32_t)KC * R * 16u;
+  const uint32_t wb = (uint32_t)p.Cp * p.Cp * 2u;
+  const int parts = p.nsplit == 3 ? 2 : 1;
+  const int nch = p.K * parts;
+  uint8_t* A_hi = smem;
+  uint8_t* A_lo = smem + a_bytes;
+  uint8_t* W0 = smem + (uint32_t)parts * a_bytes;
+  uint8_t* W1 = W0 + wb;
+
+  if (tid == 0) {
+    tc::mbar_init(&bar_a, 1);
+    tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
+    tc::mbar_init(&bar_empty[0], 1); tc::mbar_init(&bar_empty[1], 1);
+    tc::mbar_init(&bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  const uint32_t ncols = tc::tmem_cols_for(p.Cp);
+  __syncwarp();
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
   if (tid == 128) {
-    for (int i = 1; i < nch; ++i) {
+    // ---------------------------------------------------------------- producer: A image rows + weight ring
+    const uint32_t run = (uint32_t)R * 16u;
+    tc::mbar_arrive_expect_tx(&bar_a, run * KC * parts);
+    const long long row = P8_PAD + t0 - P;
+    for (int part = 0; part < parts; ++part) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(part == 0 ? p.a_hi : p.a_lo);
+      uint8_t* dst = part == 0 ? A_hi : A_lo;
+      for (int kc = 0; kc < KC; ++kc)
+        tc::bulk_g2s(dst + (size_t)kc * run, src + (((long long)b * KC + kc) * p.Lp + row) * 16, run, &bar_a);
+    }
+    for (int i = 0; i < nch; ++i) {
       const int st = i & 1;
       if (i >= 2) tc::mbar_wait(&bar_empty[st], (uint32_t)(((i >> 1) - 1) & 1));
       tc::mbar_arrive_expect_tx(&bar_full[st], wb);
-      const int tap = i / parts_w, part = i % parts_w;
+      const int tap = i / parts, part = i % parts;
       tc::bulk_g2s(st ? W1 : W0, p.wpk + ((size_t)tap * 2 + part) * wb, wb, &bar_full[st]);
     }
-  }
-  // ------------------------------------------------------------------ MMA issuer (1 thread)
-  if (tid == 160) {
+  } else if (tid == 160) {
+    // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = tc::idesc_bf16(TC_M, p.Cp);
     const uint32_t a_hi = tc::smem_u32(A_hi), a_lo = tc::smem_u32(A_lo);
     const uint32_t w_addr[2] = {tc::smem_u32(W0), tc::smem_u32(W1)};
     const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.Cp * 16u;
     uint32_t accumulate = 0;
+    tc::mbar_wait(&bar_a, 0);
     for (int i = 0; i < nch; ++i) {
       const int st = i & 1;
       tc::mbar_wait(&bar_full[st], (uint32_t)((i >> 1) & 1));
       tc::fence_after_sync();
-      const int tap = i / parts_w, part = i % parts_w;
+      const int tap = i / parts, part = i % parts;
       const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
-      const int n_a = (part == 0 && p.nsplit == 3) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
+      const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
       for (int ap = 0; ap < n_a; ++ap) {
         const uint32_t abase = (ap == 0 ? a_hi : a_lo) + row_off;
         for (int kk = 0; kk < p.Cp / 16; ++kk) {
@@ -178,10 +218,8 @@ amp_conv_tc_kernel(const AmpConvParams p) {
       tc::mma_commit(&bar_empty[st]);
     }
     tc::mma_commit(&bar_acc);
-  }
-
-  // ------------------------------------------------------------------ epilogue (warps 0-3 <-> TMEM lanes)
-  if (warp < 4) {
+  } else if (warp < 4) {
+    // ---------------------------------------------------------------- epilogue (TMEM lanes 32w..32w+31)
     tc::mbar_wait(&bar_acc, 0);
     tc::fence_after_sync();
     const int t = t0 + warp * 32 + lane;
@@ -208,15 +246,13 @@ amp_conv_tc_kernel(const AmpConvParams p) {
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, ncols);
+  if (warp == 4) tc::tmem_dealloc(tmem, ncols);
 }
 
 size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit) {
   const int R = TC_M + (K - 1) * dil;
   const size_t a = (size_t)(Cp / 8) * R * 16 * (nsplit == 3 ? 2 : 1);
-  const size_t wb = (size_t)Cp * Cp * 2;
-  const size_t staging = (size_t)8 * (3 * R + 24) * sizeof(float);
-  return a + wb + (wb > staging ? wb : staging) + 128;
+  return a + 2 * (size_t)Cp * Cp * 2 + 128;
 }
 
 int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
@@ -224,9 +260,13 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
     set_error("amp_conv_tc: bad channel padding / nsplit");
     return SVCB_E_BAD_SHAPE;
   }
+  if (p.dil * (p.K - 1) / 2 > P8_PAD || p.Lp != p8_rows_of(p.L) || !p.a_hi || (p.nsplit == 3 && !p.a_lo)) {
+    set_error("amp_conv_tc: operand image does not match (halo > 32 rows or wrong Lp)");
+    return SVCB_E_BAD_SHAPE;
+  }
   const size_t smem = amp_conv_tc_smem_bytes(p.Cp, p.K, p.dil, p.nsplit);
   if (smem > 227 * 1024 - 512) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
-  static size_t attr_bytes = 0;  // dynamic limit excludes the kernel's (small) static shared memory
+  static size_t attr_bytes = 0;  // the dynamic limit excludes the kernel's (small) static shared memory
   if (smem > attr_bytes) {
     SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem));
@@ -235,8 +275,8 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
   dim3 grid((p.L + TC_M - 1) / TC_M, p.B);
   const double macs = (double)p.B * p.L * p.C * p.C * p.K;
   KernelScope ks(p.nsplit == 3 ? "amp_conv_tc_bf16x3" : "amp_conv_tc_bf16", s, 2.0 * macs,
-                 4.0 * (double)p.B * p.C * p.L * (p.res ? 3 : 2));
-  amp_conv_tc_kernel<<<grid, TC_THREADS, smem, s>>>(p);
+                 (double)p.B * p.C * p.L * ((p.nsplit == 3 ? 4.0 : 2.0) + 4.0 * (p.res ? 2 : 1)));
+  amp_conv_tc_kernel<<<grid, 192, smem, s>>>(p);
   SVCB_LAUNCH_CHECK("amp_conv_tc");
   return SVCB_OK;
 }

@@ -39,7 +39,18 @@ struct ConvW {
   const float* w = nullptr;
   const float* b = nullptr;
   int cin = 0, cout = 0, cout_pad = 0, k = 1;
+  const uint8_t* tc = nullptr;  // tensor-core tile image (pack.py:pack_conv_tc_general) or null
+  int kch = 0, cin_pad = 0, bn = 0, ntiles = 0;
 };
+
+// must match pack.py:tc_tiling
+static void tc_tiling(ConvW& w) {
+  w.kch = (w.cin % 64 == 0) ? 64 : 32;
+  w.cin_pad = (w.cin + w.kch - 1) / w.kch * w.kch;
+  const int cp16 = (w.cout + 15) / 16 * 16;
+  w.ntiles = (cp16 + 255) / 256;
+  w.bn = ((cp16 + w.ntiles - 1) / w.ntiles + 15) / 16 * 16;
+}
 struct SnakeW { const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr; };
 
 struct EncLayer {
@@ -142,6 +153,22 @@ static ConvParams std_conv(const ConvW& w, const float* x, float* y, int B, int 
   return p;
 }
 
+// Route a stride-1 "same" convolution to the tensor cores when the model runs in a tensor-core
+// precision mode and the conv has a tile image; otherwise the fp32 CUDA-core kernel.
+static int run_conv(const svcb_model* m, const ConvW& w, const ConvParams& p, cudaStream_t s) {
+  const int prec = m->cfg.precision;
+  if (prec == 0 || !w.tc || p.stride != 1 || p.out_mul != 1 || p.out_off != 0 || p.q0 != 0 ||
+      p.syt != 1 || p.addvec || p.out_div != 0.f || p.nq != p.Tin)
+    return launch_conv1d(p, s);
+  ConvTcParams q;
+  q.x = p.x; q.sxb = p.sxb; q.sxc = p.sxc; q.sxt = p.sxt;
+  q.wpk = w.tc; q.bias = p.bias; q.y = p.y; q.res = p.res; q.lengths = p.lengths;
+  q.B = p.B; q.Cin = p.Cin; q.cin_pad = w.cin_pad; q.Cout = p.Cout; q.Tin = p.Tin; q.Tout = p.nq;
+  q.K = p.K; q.dil = p.dil; q.pad = p.pad; q.kch = w.kch; q.bn = w.bn; q.ntiles = w.ntiles;
+  q.nsplit = prec == 1 ? 1 : 3; q.flags = p.flags; q.act = p.act;
+  return launch_conv_tc(q, s);
+}
+
 __global__ void mask_mul_kernel(float* __restrict__ x, const long long* __restrict__ lengths, int C,
                                 int T) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y, b = blockIdx.z;
@@ -173,34 +200,34 @@ static int run_prior(const svcb_model* m, Ctx& ctx, const float* ppg, const floa
     ConvParams p = std_conv(m->pre, ppg, x, B, T, T, 2);
     p.sxb = (long long)T * c.ppg_dim; p.sxc = 1; p.sxt = c.ppg_dim;
     p.lengths = lengths; p.flags = CONV_OUT_MASK;
-    RUN(launch_conv1d(p, s));
+    RUN(run_conv(m, m->pre, p, s));
     ConvParams q = std_conv(m->hub, vec, x, B, T, T, 2);
     q.sxb = (long long)T * c.vec_dim; q.sxc = 1; q.sxt = c.vec_dim;
     q.lengths = lengths; q.flags = CONV_OUT_MASK; q.res = x;
-    RUN(launch_conv1d(q, s));
+    RUN(run_conv(m, m->hub, q, s));
   }
   RUN(launch_pitch_embed_add(x, pit, m->pit_emb, B, H, T, s));
   SVCB_TRY(tap(ctx, SVCB_TAP_ENC_FRONT, x, (size_t)B * H * T));
   RUN(launch_mask_mul(x, lengths, B, H, T, s));  // Encoder.forward: x = x * x_mask
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayer& L = m->enc[i];
-    RUN(launch_conv1d(std_conv(L.qkv, x, qkv, B, T, T, 0), s));
+    RUN(run_conv(m, L.qkv, std_conv(L.qkv, x, qkv, B, T, T, 0), s));
     RUN(launch_rel_attention(qkv, L.ek, L.ev, lengths, att, B, H, c.enc_heads, c.enc_window, T, s));
-    RUN(launch_conv1d(std_conv(L.o, att, y, B, T, T, 0), s));
+    RUN(run_conv(m, L.o, std_conv(L.o, att, y, B, T, T, 0), s));
     RUN(launch_layernorm_c(x, y, L.ln1g, L.ln1b, x, B, H, T, 0, 1e-5f, s));
     const int pl = (c.enc_kernel - 1) / 2;
     ConvParams f1 = std_conv(L.ffn1, x, hbuf, B, T, T, pl);
     f1.lengths = lengths; f1.flags = CONV_IN_MASK; f1.act = ACT_RELU;
-    RUN(launch_conv1d(f1, s));
+    RUN(run_conv(m, L.ffn1, f1, s));
     ConvParams f2 = std_conv(L.ffn2, hbuf, y, B, T, T, pl);
     f2.lengths = lengths; f2.flags = CONV_IN_MASK | CONV_OUT_MASK;
-    RUN(launch_conv1d(f2, s));
+    RUN(run_conv(m, L.ffn2, f2, s));
     RUN(launch_layernorm_c(x, y, L.ln2g, L.ln2b, x, B, H, T, 0, 1e-5f, s));
     if (i < 6) SVCB_TRY(tap(ctx, SVCB_TAP_ENC_LAYER0 + i, x, (size_t)B * H * T));
   }
   ConvParams pj = std_conv(m->proj, x, stats, B, T, T, 0);
   pj.lengths = lengths; pj.flags = CONV_IN_MASK | CONV_OUT_MASK;
-  RUN(launch_conv1d(pj, s));
+  RUN(run_conv(m, m->proj, pj, s));
   RUN(launch_reparam(stats, eps, lengths, z_p, B, C, T, s));
   SVCB_TRY(tap(ctx, SVCB_TAP_ZP, z_p, (size_t)B * C * T));
   return SVCB_OK;
@@ -230,19 +257,19 @@ static int run_flow(const svcb_model* m, Ctx& ctx, const float* z_p, const long 
     RUN(launch_coupling_pre(cur, sp, lengths, Y, x0n, B, C, T, s));
     ConvParams pp = std_conv(F.pre, x0n, h, B, T, T, 0);
     pp.lengths = lengths; pp.flags = CONV_OUT_MASK;
-    RUN(launch_conv1d(pp, s));
+    RUN(run_conv(m, F.pre, pp, s));
     const int nl = c.wn_layers;
     for (int l = 0; l < nl; ++l) {
       ConvParams pi = std_conv(F.in[l], h, g, B, T, T, (c.wn_kernel - 1) / 2);
       pi.flags = CONV_GATE;
       pi.syb = (long long)H * T;  // gated output has H channels
-      RUN(launch_conv1d(pi, s));
-      RUN(launch_conv1d(std_conv(F.rs[l], g, rs, B, T, T, 0), s));
+      RUN(run_conv(m, F.in[l], pi, s));
+      RUN(run_conv(m, F.rs[l], std_conv(F.rs[l], g, rs, B, T, T, 0), s));
       RUN(launch_wn_update(h, out, rs, lengths, B, H, T, l == 0, l == nl - 1, s));
     }
     ConvParams po = std_conv(F.post, out, mm, B, T, T, 0);
     po.lengths = lengths; po.flags = CONV_OUT_MASK;
-    RUN(launch_conv1d(po, s));
+    RUN(run_conv(m, F.post, po, s));
     RUN(launch_coupling_post(cur, sp, mm, lengths, Y, B, C, T, s));
     if (f < 4) SVCB_TRY(tap(ctx, SVCB_TAP_FLOW0 + f, Y, (size_t)B * C * T));
     cur = Y;
@@ -252,7 +279,8 @@ static int run_flow(const svcb_model* m, Ctx& ctx, const float* z_p, const long 
 
 // ----------------------------------------------------------------------------- generator
 static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* X, float* ACC,
-                         float* T1, float* T2, float* RA, float* RB, int B, int ch, int L) {
+                         float* T1, float* T2, float* RA, float* RB, void* IMG_HI, void* IMG_LO, int B,
+                         int ch, int L) {
   cudaStream_t s = ctx.stream;
   const int nres = m->cfg.n_res;
   const int prec = m->cfg.precision;
@@ -262,13 +290,15 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
     for (int d = 0; d < 3; ++d) {
       const SnakeW& a1 = R.act[2 * d];
       const SnakeW& a2 = R.act[2 * d + 1];
-      if (prec != 0) {  // tensor-core path: SnakeAlias fused into each conv's operand staging
+      if (prec != 0) {  // tensor-core path: snake_pack -> amp_conv_tc, twice per unit
         AmpConvParams q;
         q.B = B; q.C = ch; q.Cp = (ch + 15) / 16 * 16; q.L = L; q.K = R.k; q.nsplit = prec == 1 ? 1 : 3;
-        q.x = cur; q.y = T2; q.ea = a1.ea; q.ib = a1.ib; q.fu = a1.fu; q.fd = a1.fd;
-        q.wpk = R.c1_tc[d]; q.bias = R.c1[d].b; q.dil = R.dil[d];
+        q.Lp = p8_rows(L); q.a_hi = IMG_HI; q.a_lo = q.nsplit == 3 ? IMG_LO : nullptr;
+        void* lo = q.nsplit == 3 ? IMG_LO : nullptr;
+        RUN(launch_snake_pack(cur, IMG_HI, lo, a1.ea, a1.ib, a1.fu, a1.fd, B, ch, L, s));
+        q.y = T2; q.wpk = R.c1_tc[d]; q.bias = R.c1[d].b; q.dil = R.dil[d];
         RUN(launch_amp_conv_tc(q, s));
-        q.x = T2; q.ea = a2.ea; q.ib = a2.ib; q.fu = a2.fu; q.fd = a2.fd;
+        RUN(launch_snake_pack(T2, IMG_HI, lo, a2.ea, a2.ib, a2.fu, a2.fd, B, ch, L, s));
         q.wpk = R.c2_tc[d]; q.bias = R.c2[d].b; q.dil = 1; q.res = cur;
         if (d < 2) {
           q.y = (d == 0) ? RA : RB;
@@ -320,6 +350,13 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
   float* T2 = ctx.alloc<float>(max_stage);
   float* RA = ctx.alloc<float>(max_stage);
   float* RB = ctx.alloc<float>(max_stage);
+  size_t img_bytes = 0;
+  if (c.precision != 0) {
+    int ch = c.gen_initial_channel; long long L = T;
+    for (int i = 0; i < c.n_ups; ++i) { ch /= 2; L *= c.up_rates[i]; img_bytes = std::max<size_t>(img_bytes, p8_image_bytes(B, ch, (int)L)); }
+  }
+  void* IMG_HI = img_bytes ? ctx.alloc<uint8_t>(img_bytes) : nullptr;
+  void* IMG_LO = (img_bytes && c.precision != 1) ? ctx.alloc<uint8_t>(img_bytes) : nullptr;
   SVCB_TRY(check_ws(ctx));
 
   RUN(launch_linear_small(spk, m->ad_sw, m->ad_sb, sc, B, c.spk_dim, U, s));
@@ -328,7 +365,7 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
   {
     ConvParams p = std_conv(m->conv_pre, xa, x0, B, T, T, 3);
     p.act = ACT_MISH;
-    RUN(launch_conv1d(p, s));
+    RUN(run_conv(m, m->conv_pre, p, s));
   }
   SVCB_TRY(tap(ctx, SVCB_TAP_GEN_PRE, x0, (size_t)B * c.gen_initial_channel * T));
 
@@ -366,7 +403,7 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
       RUN(launch_conv1d(p, s));
     }
     SVCB_TRY(tap(ctx, SVCB_TAP_GEN_UP0 + i, X, (size_t)B * chn * Ln));
-    SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, B, chn, Ln));
+    SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, IMG_HI, IMG_LO, B, chn, Ln));
     SVCB_TRY(tap(ctx, SVCB_TAP_GEN_STAGE0 + i, ACC, (size_t)B * chn * Ln));
     x = ACC; ch = chn; L = Ln;
   }
@@ -394,11 +431,16 @@ struct Resolver {
     }
     return it->second.first;
   }
-  ConvW conv(const std::string& prefix, int cin, int cout, int k, bool bias = true) {
+  ConvW conv(const std::string& prefix, int cin, int cout, int k, bool bias = true, bool tc = false) {
     ConvW w;
     w.cin = cin; w.cout = cout; w.k = k; w.cout_pad = (cout + 7) / 8 * 8;
     w.w = get(prefix + ".w", (uint64_t)cin * k * w.cout_pad);
     w.b = bias ? get(prefix + ".b", cout) : nullptr;
+    if (tc) {
+      tc_tiling(w);
+      const uint64_t numel = (uint64_t)k * 2 * w.cin_pad * w.ntiles * w.bn / 2;
+      w.tc = reinterpret_cast<const uint8_t*>(get(prefix + ".tc", numel));
+    }
     return w;
   }
   SnakeW snake(const std::string& prefix, int ch) {
@@ -413,34 +455,34 @@ static int resolve(svcb_model* m) {
   const svcb_config& c = m->cfg;
   Resolver R{m};
   const int H = c.hidden_channels, C = c.inter_channels;
-  m->pre = R.conv("enc_p.pre", c.ppg_dim, H, 5);
-  m->hub = R.conv("enc_p.hub", c.vec_dim, H, 5);
+  m->pre = R.conv("enc_p.pre", c.ppg_dim, H, 5, true, true);
+  m->hub = R.conv("enc_p.hub", c.vec_dim, H, 5, true, true);
   m->pit_emb = R.get("enc_p.pit", 256ull * H);
   m->enc.resize(c.enc_layers);
   for (int i = 0; i < c.enc_layers; ++i) {
     const std::string p = "enc." + std::to_string(i);
     EncLayer& L = m->enc[i];
-    L.qkv = R.conv(p + ".qkv", H, 3 * H, 1);
-    L.o = R.conv(p + ".o", H, H, 1);
-    L.ffn1 = R.conv(p + ".ffn1", H, c.filter_channels, c.enc_kernel);
-    L.ffn2 = R.conv(p + ".ffn2", c.filter_channels, H, c.enc_kernel);
+    L.qkv = R.conv(p + ".qkv", H, 3 * H, 1, true, true);
+    L.o = R.conv(p + ".o", H, H, 1, true, true);
+    L.ffn1 = R.conv(p + ".ffn1", H, c.filter_channels, c.enc_kernel, true, true);
+    L.ffn2 = R.conv(p + ".ffn2", c.filter_channels, H, c.enc_kernel, true, true);
     const uint64_t nr = (uint64_t)(2 * c.enc_window + 1) * (H / c.enc_heads);
     L.ek = R.get(p + ".ek", nr); L.ev = R.get(p + ".ev", nr);
     L.ln1g = R.get(p + ".ln1.g", H); L.ln1b = R.get(p + ".ln1.b", H);
     L.ln2g = R.get(p + ".ln2.g", H); L.ln2b = R.get(p + ".ln2.b", H);
   }
-  m->proj = R.conv("enc_p.proj", H, 2 * C, 1);
+  m->proj = R.conv("enc_p.proj", H, 2 * C, 1, true, true);
   m->flow.resize(c.n_flows);
   for (int f = 0; f < c.n_flows; ++f) {
     const std::string p = "flow." + std::to_string(f);
     FlowLayer& F = m->flow[f];
-    F.pre = R.conv(p + ".pre", C / 2, H, 1);
-    F.post = R.conv(p + ".post", H, C / 2, 1);
+    F.pre = R.conv(p + ".pre", C / 2, H, 1, true, true);
+    F.post = R.conv(p + ".post", H, C / 2, 1, true, true);
     F.snac_w = R.get(p + ".snac.w", (uint64_t)C * c.spk_dim);
     F.snac_b = R.get(p + ".snac.b", C);
     for (int l = 0; l < c.wn_layers; ++l) {
-      F.in.push_back(R.conv(p + ".in." + std::to_string(l), H, 2 * H, c.wn_kernel));
-      F.rs.push_back(R.conv(p + ".rs." + std::to_string(l), H, l + 1 < c.wn_layers ? 2 * H : H, 1));
+      F.in.push_back(R.conv(p + ".in." + std::to_string(l), H, 2 * H, c.wn_kernel, true, true));
+      F.rs.push_back(R.conv(p + ".rs." + std::to_string(l), H, l + 1 < c.wn_layers ? 2 * H : H, 1, true, true));
     }
   }
   const int U = c.gen_input;
@@ -448,7 +490,7 @@ static int resolve(svcb_model* m) {
   m->ad_sb = R.get("dec.adapter.scale.b", U);
   m->ad_bw = R.get("dec.adapter.bias.w", (uint64_t)U * c.spk_dim);
   m->ad_bb = R.get("dec.adapter.bias.b", U);
-  m->conv_pre = R.conv("dec.conv_pre", U, c.gen_initial_channel, 7);
+  m->conv_pre = R.conv("dec.conv_pre", U, c.gen_initial_channel, 7, true, true);
   m->merge_w = R.get("dec.merge_w", c.n_harmonics);
   m->merge_b = R.get("dec.merge_b", 1);
   m->ups.resize(c.n_ups);
@@ -709,15 +751,43 @@ int svcb_op_conv1d(const float* x, const float* w_packed, const float* bias, flo
   return launch_conv1d(p, static_cast<cudaStream_t>(stream));
 }
 
+int svcb_op_conv_tc(const float* x, const void* w_tc, const float* bias, float* y, const float* res,
+                    const int64_t* lengths, int32_t B, int32_t Cin, int32_t Cout, int32_t T, int32_t K,
+                    int32_t dilation, int32_t nsplit, int32_t flags, int32_t act, svcb_stream stream) {
+  g_launches = 0;
+  ConvW w; w.cin = Cin; w.cout = Cout; w.k = K;
+  tc_tiling(w);
+  ConvTcParams q;
+  q.x = x; q.sxb = (long long)Cin * T; q.sxc = T; q.sxt = 1;
+  q.wpk = static_cast<const uint8_t*>(w_tc); q.bias = bias; q.y = y; q.res = res;
+  q.lengths = reinterpret_cast<const long long*>(lengths);
+  q.B = B; q.Cin = Cin; q.cin_pad = w.cin_pad; q.Cout = Cout; q.Tin = T; q.Tout = T;
+  q.K = K; q.dil = dilation; q.pad = dilation * (K - 1) / 2; q.kch = w.kch; q.bn = w.bn; q.ntiles = w.ntiles;
+  q.nsplit = nsplit; q.flags = flags; q.act = act;
+  return launch_conv_tc(q, static_cast<cudaStream_t>(stream));
+}
+
+size_t svcb_op_amp_conv_tc_scratch_bytes(int32_t B, int32_t C, int32_t L) { return 2 * p8_image_bytes(B, C, L) + 512; }
+
 int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float* ea, const float* inv_b,
                         const float* fu, const float* fd, const void* w_tc, const float* bias, int32_t B,
-                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit, svcb_stream stream) {
+                        int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit, void* scratch,
+                        size_t scratch_bytes, svcb_stream stream) {
   g_launches = 0;
+  const size_t img = (p8_image_bytes(B, C, L) + 255) & ~(size_t)255;
+  if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < 2 * img) {
+    set_error("svcb_op_amp_conv_tc: scratch too small or misaligned");
+    return SVCB_E_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  void* hi = scratch;
+  void* lo = nsplit == 3 ? static_cast<char*>(scratch) + img : nullptr;
+  SVCB_TRY(launch_snake_pack(x, hi, lo, ea, inv_b, fu, fd, B, C, L, s));
   AmpConvParams q;
-  q.x = x; q.y = y; q.res = res; q.ea = ea; q.ib = inv_b; q.fu = fu; q.fd = fd;
+  q.a_hi = hi; q.a_lo = lo; q.Lp = p8_rows(L); q.y = y; q.res = res;
   q.wpk = static_cast<const uint8_t*>(w_tc); q.bias = bias;
   q.B = B; q.C = C; q.Cp = (C + 15) / 16 * 16; q.L = L; q.K = K; q.dil = dilation; q.nsplit = nsplit;
-  return launch_amp_conv_tc(q, static_cast<cudaStream_t>(stream));
+  return launch_amp_conv_tc(q, s);
 }
 
 int svcb_op_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,

@@ -78,10 +78,11 @@ int launch_conv1d(const ConvParams& p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- tensor-core AMP conv
 struct AmpConvParams {
-  const float* x = nullptr;     // [B, C, L]
+  const void* a_hi = nullptr;   // operand image bf16 [B][Cp/8][Lp][8] written by snake_pack
+  const void* a_lo = nullptr;   // low split part (nsplit == 3) or null
+  int Lp = 0;                   // image rows = p8_rows(L)
   float* y = nullptr;           // [B, C, L]
   const float* res = nullptr;   // residual [B, C, L] or null
-  const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;  // SnakeAlias parameters
   const uint8_t* wpk = nullptr; // bf16 [K][2 (hi,lo)][Cp/8][Cp][8]  (pack.py:pack_conv_tc)
   const float* bias = nullptr;  // [C]
   int B = 0, C = 0, Cp = 0, L = 0, K = 1, dil = 1;
@@ -91,6 +92,28 @@ struct AmpConvParams {
 };
 int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s);
 size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit);
+// SnakeAlias(x[B,C,L]) -> bf16 hi (and lo, may be null) operand images
+int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
+                      const float* fd, int B, int C, int L, cudaStream_t s);
+size_t p8_image_bytes(int B, int C, int L);
+int p8_rows(int L);
+
+// ----------------------------------------------------------------------------- general tensor-core conv
+struct ConvTcParams {
+  const float* x = nullptr;
+  long long sxb = 0, sxc = 0, sxt = 1;   // element strides of x[b, ci, t]
+  const uint8_t* wpk = nullptr;          // bf16 tiles [K][ncc][2][ntiles][kch/8][bn][8] (pack.py:pack_conv_tc_general)
+  const float* bias = nullptr;           // [Cout] (packed order) or null
+  float* y = nullptr;                    // [B, Cout(/2 if gated), Tout] contiguous
+  const float* res = nullptr;            // indexed like y, or null
+  const long long* lengths = nullptr;
+  int B = 0, Cin = 0, cin_pad = 0, Cout = 0, Tin = 0, Tout = 0;
+  int K = 1, dil = 1, pad = 0;
+  int kch = 64, bn = 128, ntiles = 1;
+  int nsplit = 3;
+  int flags = 0, act = 0;
+};
+int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
 
 // ----------------------------------------------------------------------------- snake alias
 int launch_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,

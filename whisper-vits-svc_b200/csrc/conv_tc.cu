@@ -1,0 +1,242 @@
+// General Conv1d as an implicit GEMM on tcgen05/TMEM (bf16 or bf16x3 operands, fp32 accumulate).
+//
+// Serves every dense convolution of the prior encoder, the flow and the generator head
+// (vits/models.py:44-49, vits/attentions.py:215-223,390-398, vits/modules.py:184-198,296-299,
+// vits_decoder/generator.py:177-178) — the F.conv1d call sites whose contraction is wide enough for
+// the tensor cores.
+//
+//   D[t, co] = sum_cc sum_tap  A_cc[t + tap*dil, :] . W[tap, cc][co, :]      M = 128, N = BN, K = KCH
+// * Input channels are processed in chunks of KCH (32 or 64).  Four producer warps gather one
+//   chunk of x (fp32, any strides — the time-major PPG input included), apply the optional input
+//   mask and the conv's zero padding, split to bf16 hi/lo and write the K-major panel layout of
+//   tc.cuh into a 2-deep A ring (generic proxy -> fence.proxy.async -> mbarrier).
+// * For every (chunk, tap) the pre-packed weight tiles (hi, lo) arrive by 1-D bulk copy into a
+//   3-deep W ring.  One thread issues the MMAs: taps reuse the same A chunk through a row-shifted
+//   descriptor; tcgen05.commit releases W slots and A buffers.
+// * Epilogue (the producer warps again): tcgen05.ld -> bias -> {none, ReLU, Mish, tanh, WaveNet
+//   gate on interleaved channel pairs} -> output mask -> residual -> accumulate -> store [B,C,T].
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace svcb {
+
+constexpr int CT_M = 128;
+constexpr int CT_WST = 3;  // W ring depth
+
+__device__ __forceinline__ float ct_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.f);
+    case ACT_MISH: { const float sp = v > 20.f ? v : log1pf(expf(v)); return v * tanhf(sp); }
+    case ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+    case ACT_TANH: return tanhf(v);
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ void ct_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv_tc_kernel(const ConvTcParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[CT_WST], w_empty[CT_WST], bar_acc;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, nt = blockIdx.y;
+  const int t0 = blockIdx.x * CT_M;
+  const int P = p.pad;
+  const int R = CT_M + (p.K - 1) * p.dil;
+  const int KC = p.kch / 8;
+  const int n0row = t0 - P;                       // sequence position of A row 0
+  const uint32_t a_part = (uint32_t)KC * R * 16u; // one of hi / lo
+  const int nparts = p.nsplit == 3 ? 2 : 1;
+  const uint32_t a_buf = a_part * nparts;
+  const uint32_t w_tile = (uint32_t)p.kch * p.bn * 2u;
+  uint8_t* A0 = smem;
+  uint8_t* W0 = smem + 2 * a_buf;
+  const int ncc = p.cin_pad / p.kch;
+  const long long len = p.lengths ? p.lengths[b] : (long long)1 << 60;
+
+  if (tid == 0) {
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < CT_WST; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    tc::mbar_init(&bar_acc, 1);
+    tc::fence_barrier_init();
+  }
+  const uint32_t ncols = tc::tmem_cols_for(p.bn);
+  __syncwarp();
+  if (warp == 4) tc::tmem_alloc(&tmem_slot, ncols);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- A producers
+    const float* xb = p.x + (long long)b * p.sxb;
+    for (int cc = 0; cc < ncc; ++cc) {
+      const int buf = cc & 1;
+      if (cc >= 2) tc::mbar_wait(&a_empty[buf], (uint32_t)(((cc >> 1) - 1) & 1));
+      uint8_t* Ah = A0 + (size_t)buf * a_buf;
+      uint8_t* Al = Ah + a_part;
+      for (int item = tid; item < R * KC; item += 128) {
+        const int r = item % R, kc = item / R;
+        const int tau = n0row + r;
+        const int c0 = cc * p.kch + kc * 8;
+        float v[8];
+        const bool row_ok = tau >= 0 && tau < p.Tin && (!(p.flags & CONV_IN_MASK) || tau < len);
+        if (row_ok) {
+          if (p.sxc == 1 && c0 + 8 <= p.Cin) {  // channel-contiguous input: two 16-byte loads
+            const float4* s4 = reinterpret_cast<const float4*>(xb + (long long)tau * p.sxt + c0);
+            const float4 u0 = __ldg(s4), u1 = __ldg(s4 + 1);
+            v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              v[e] = (c0 + e < p.Cin) ? __ldg(xb + (long long)(c0 + e) * p.sxc + (long long)tau * p.sxt) : 0.f;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = 0.f;
+        }
+        __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          hi[e] = __float2bfloat16_rn(v[e]);
+          lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+        }
+        *reinterpret_cast<uint4*>(Ah + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(hi);
+        if (nparts == 2)
+          *reinterpret_cast<uint4*>(Al + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(lo);
+      }
+      tc::fence_proxy_async_smem();
+      ct_arrive(&a_full[buf]);
+    }
+    // ---------------------------------------------------------------- epilogue
+    tc::mbar_wait(&bar_acc, 0);
+    tc::fence_after_sync();
+    const int t = t0 + warp * 32 + lane;
+    const bool gate = (p.flags & CONV_GATE) != 0;
+    const int cout_real = gate ? p.Cout / 2 : p.Cout;
+    const bool keep = !(p.flags & CONV_OUT_MASK) || t < len;
+    float* yb = p.y + (long long)b * cout_real * p.Tout;
+    const float* rb = p.res ? p.res + (long long)b * cout_real * p.Tout : nullptr;
+    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld_wait();
+      if (t < p.Tout) {
+        auto finish = [&](float o, int co) {
+          if (!keep) o = 0.f;
+          const long long off = (long long)co * p.Tout + t;
+          if (rb) o += rb[off];
+          if (p.flags & CONV_ACCUM) o += yb[off];
+          yb[off] = o;
+        };
+        if (gate) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 2) {
+            const int cp = nt * p.bn + c0 + j;
+            if (cp + 1 < p.Cout) {
+              const float a = __uint_as_float(v[j]) + __ldg(p.bias + cp);
+              const float g = __uint_as_float(v[j + 1]) + __ldg(p.bias + cp + 1);
+              finish(tanhf(a) * (1.f / (1.f + expf(-g))), cp >> 1);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int co = nt * p.bn + c0 + j;
+            if (co < p.Cout) {
+              float o = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + co) : 0.f);
+              finish(ct_act(o, p.act), co);
+            }
+          }
+        }
+      }
+    }
+  } else if (tid == 128) {
+    // ---------------------------------------------------------------- W producer
+    const int total = ncc * p.K * nparts;
+    for (int i = 0; i < total; ++i) {
+      const int st = i % CT_WST;
+      if (i >= CT_WST) tc::mbar_wait(&w_empty[st], (uint32_t)(((i / CT_WST) - 1) & 1));
+      const int part = i % nparts, tap = (i / nparts) % p.K, cc = i / (nparts * p.K);
+      const size_t tile = (((size_t)tap * ncc + cc) * 2 + part) * p.ntiles + nt;
+      tc::mbar_arrive_expect_tx(&w_full[st], w_tile);
+      tc::bulk_g2s(W0 + (size_t)st * w_tile, p.wpk + tile * w_tile, w_tile, &w_full[st]);
+    }
+  } else if (tid == 160) {
+    // ---------------------------------------------------------------- MMA issuer
+    const uint32_t idesc = tc::idesc_bf16(CT_M, p.bn);
+    const uint32_t a_base = tc::smem_u32(A0), w_base = tc::smem_u32(W0);
+    const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.bn * 16u;
+    uint32_t accumulate = 0;
+    int wi = 0;
+    for (int cc = 0; cc < ncc; ++cc) {
+      const int buf = cc & 1;
+      tc::mbar_wait(&a_full[buf], (uint32_t)((cc >> 1) & 1));
+      tc::fence_after_sync();
+      const uint32_t ah = a_base + (uint32_t)buf * a_buf, al = ah + a_part;
+      for (int tap = 0; tap < p.K; ++tap) {
+        const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
+        for (int part = 0; part < nparts; ++part, ++wi) {
+          const int st = wi % CT_WST;
+          tc::mbar_wait(&w_full[st], (uint32_t)((wi / CT_WST) & 1));
+          tc::fence_after_sync();
+          const uint32_t wb = w_base + (uint32_t)st * w_tile;
+          const int n_a = (part == 0 && nparts == 2) ? 2 : 1;
+          for (int ap = 0; ap < n_a; ++ap) {
+            const uint32_t ab = (ap == 0 ? ah : al) + row_off;
+            for (int kk = 0; kk < p.kch / 16; ++kk) {
+              const uint64_t ad = tc::smem_desc(ab + (uint32_t)kk * 2u * lbo_a, lbo_a);
+              const uint64_t bd = tc::smem_desc(wb + (uint32_t)kk * 2u * lbo_b, lbo_b);
+              tc::mma_bf16(tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          tc::mma_commit(&w_empty[st]);
+        }
+      }
+      tc::mma_commit(&a_empty[buf]);
+    }
+    tc::mma_commit(&bar_acc);
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+}
+
+size_t conv_tc_smem_bytes(const ConvTcParams& p) {
+  const int R = CT_M + (p.K - 1) * p.dil;
+  const size_t a_buf = (size_t)(p.kch / 8) * R * 16 * (p.nsplit == 3 ? 2 : 1);
+  return 2 * a_buf + (size_t)CT_WST * p.kch * p.bn * 2 + 128;
+}
+
+int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
+  if (p.B <= 0 || p.Tout <= 0) return SVCB_OK;
+  if ((p.kch != 32 && p.kch != 64) || p.cin_pad % p.kch || p.bn % 16 || p.bn < 16 || p.bn > 256 ||
+      p.ntiles * p.bn < p.Cout || (p.nsplit != 1 && p.nsplit != 3) || p.Tout != p.Tin) {
+    set_error("conv_tc: unsupported tiling (stride-1 'same' convolutions only)");
+    return SVCB_E_BAD_SHAPE;
+  }
+  const size_t smem = conv_tc_smem_bytes(p);
+  if (smem > 227 * 1024 - 512) { set_error("conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  dim3 grid((p.Tout + CT_M - 1) / CT_M, p.ntiles, p.B);
+  const int cout_real = (p.flags & CONV_GATE) ? p.Cout / 2 : p.Cout;
+  KernelScope ks(p.nsplit == 3 ? "conv_tc_bf16x3" : "conv_tc_bf16", s,
+                 2.0 * p.Cin * p.K * p.Cout * (double)p.Tout * p.B,
+                 4.0 * ((double)p.B * p.Cin * p.Tin + (double)p.B * cout_real * p.Tout * (p.res ? 2 : 1)) +
+                     2.0 * (double)p.Cin * p.K * p.Cout);
+  conv_tc_kernel<<<grid, 192, smem, s>>>(p);
+  SVCB_LAUNCH_CHECK("conv_tc");
+  return SVCB_OK;
+}
+
+}  // namespace svcb

@@ -85,8 +85,30 @@ def amp_conv_tc(x, alpha, beta, fu, fd, weight, bias, dilation=1, res=None, nspl
     b = _c(bias)
     r = _c(res) if res is not None else None
     y = torch.empty_like(x)
-    st = _lib.load().svcb_op_amp_conv_tc(x.data_ptr(), y.data_ptr(), r.data_ptr() if r is not None else None,
-                                         ea.data_ptr(), ib.data_ptr(), fu.data_ptr(), fd.data_ptr(),
-                                         wtc.data_ptr(), b.data_ptr(), B, C, L, K, dilation, nsplit, _s())
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.svcb_op_amp_conv_tc_scratch_bytes(B, C, L)), dtype=torch.uint8, device=x.device)
+    st = lib.svcb_op_amp_conv_tc(x.data_ptr(), y.data_ptr(), r.data_ptr() if r is not None else None,
+                                 ea.data_ptr(), ib.data_ptr(), fu.data_ptr(), fd.data_ptr(),
+                                 wtc.data_ptr(), b.data_ptr(), B, C, L, K, dilation, nsplit,
+                                 scratch.data_ptr(), scratch.numel(), _s())
     _lib.check(st, "svcb_op_amp_conv_tc")
+    return y
+
+
+def conv_tc(x, weight, bias=None, dilation=1, res=None, lengths=None, nsplit=3, flags=0, act=0):
+    """Stride-1 'same' Conv1d on the tensor cores; weight in torch layout [Cout,Cin,K]."""
+    x = _c(x)
+    B, Cin, T = x.shape
+    Cout, _, K = weight.shape
+    wtc = pack.pack_conv_tc_general(weight.detach().cpu().float()).to(x.device)
+    b = _c(bias) if bias is not None else None
+    r = _c(res) if res is not None else None
+    ln = lengths.to(x.device, torch.int64).contiguous() if lengths is not None else None
+    cout_real = Cout // 2 if (flags & 4) else Cout
+    y = torch.zeros(B, cout_real, T, device=x.device)
+    st = _lib.load().svcb_op_conv_tc(x.data_ptr(), wtc.data_ptr(), b.data_ptr() if b is not None else None,
+                                     y.data_ptr(), r.data_ptr() if r is not None else None,
+                                     ln.data_ptr() if ln is not None else None, B, Cin, Cout, T, K, dilation,
+                                     nsplit, flags, act, _s())
+    _lib.check(st, "svcb_op_conv_tc")
     return y

@@ -63,6 +63,33 @@ def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
     return img.view(torch.float32).reshape(-1)
 
 
+def tc_tiling(cout: int, cin: int):
+    """(kch, cin_pad, bn, ntiles) — must match csrc/api.cu:tc_tiling."""
+    kch = 64 if cin % 64 == 0 else 32
+    cin_pad = (cin + kch - 1) // kch * kch
+    cp16 = (cout + 15) // 16 * 16
+    ntiles = (cp16 + 255) // 256
+    bn = ((cp16 + ntiles - 1) // ntiles + 15) // 16 * 16
+    return kch, cin_pad, bn, ntiles
+
+
+def pack_conv_tc_general(w: torch.Tensor) -> torch.Tensor:
+    """[Cout, Cin, K] fp32 -> bf16 tiles [K][ncc][2 (hi,lo)][ntiles][kch/8][bn][8] for
+    csrc/conv_tc.cu: per (tap, input-channel chunk, split part, output tile) the B operand
+    W[n = co][k = ci] in the K-major panel layout, one contiguous bulk copy each."""
+    cout, cin, k = w.shape
+    kch, cin_pad, bn, ntiles = tc_tiling(cout, cin)
+    ncc = cin_pad // kch
+    wp = torch.zeros(k, ntiles * bn, cin_pad, dtype=torch.float32)
+    wp[:, :cout, :cin] = w.permute(2, 0, 1)
+    hi = wp.bfloat16()
+    lo = (wp - hi.float()).bfloat16()
+    st = torch.stack([hi, lo], 1)                               # [K, 2, N, Kin]
+    st = st.view(k, 2, ntiles, bn, ncc, kch // 8, 8)            # K, part, nt, n, cc, kc, e
+    img = st.permute(0, 4, 1, 2, 5, 3, 6).contiguous()          # K, cc, part, nt, kc, n, e
+    return img.view(torch.float32).reshape(-1)
+
+
 def config_from_hp(hp, precision: int = 0) -> dict:
     rates = [int(x) for x in hp.gen.upsample_rates]
     ks = [int(x) for x in hp.gen.upsample_kernel_sizes]
@@ -87,44 +114,46 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
     def put(name, t):
         out.append((name, t.detach().float().contiguous()))
 
-    def conv(name, w, b=None):
+    def conv(name, w, b=None, tc=False):
         put(name + ".w", pack_conv(w))
         if b is not None:
             put(name + ".b", b)
+        if tc:
+            put(name + ".tc", pack_conv_tc_general(w))
 
     H = cfg["hidden_channels"]
-    conv("enc_p.pre", sd["enc_p.pre.weight"], sd["enc_p.pre.bias"])
-    conv("enc_p.hub", sd["enc_p.hub.weight"], sd["enc_p.hub.bias"])
+    conv("enc_p.pre", sd["enc_p.pre.weight"], sd["enc_p.pre.bias"], tc=True)
+    conv("enc_p.hub", sd["enc_p.hub.weight"], sd["enc_p.hub.bias"], tc=True)
     put("enc_p.pit", sd["enc_p.pit.weight"])
     for i in range(cfg["enc_layers"]):
         a = f"enc_p.enc.attn_layers.{i}"
         wq = torch.cat([sd[f"{a}.conv_{n}.weight"] for n in "qkv"], 0)
         bq = torch.cat([sd[f"{a}.conv_{n}.bias"] for n in "qkv"], 0)
-        conv(f"enc.{i}.qkv", wq, bq)
-        conv(f"enc.{i}.o", sd[f"{a}.conv_o.weight"], sd[f"{a}.conv_o.bias"])
+        conv(f"enc.{i}.qkv", wq, bq, tc=True)
+        conv(f"enc.{i}.o", sd[f"{a}.conv_o.weight"], sd[f"{a}.conv_o.bias"], tc=True)
         put(f"enc.{i}.ek", sd[f"{a}.emb_rel_k"][0])
         put(f"enc.{i}.ev", sd[f"{a}.emb_rel_v"][0])
         put(f"enc.{i}.ln1.g", sd[f"enc_p.enc.norm_layers_1.{i}.gamma"])
         put(f"enc.{i}.ln1.b", sd[f"enc_p.enc.norm_layers_1.{i}.beta"])
         f = f"enc_p.enc.ffn_layers.{i}"
-        conv(f"enc.{i}.ffn1", sd[f"{f}.conv_1.weight"], sd[f"{f}.conv_1.bias"])
-        conv(f"enc.{i}.ffn2", sd[f"{f}.conv_2.weight"], sd[f"{f}.conv_2.bias"])
+        conv(f"enc.{i}.ffn1", sd[f"{f}.conv_1.weight"], sd[f"{f}.conv_1.bias"], tc=True)
+        conv(f"enc.{i}.ffn2", sd[f"{f}.conv_2.weight"], sd[f"{f}.conv_2.bias"], tc=True)
         put(f"enc.{i}.ln2.g", sd[f"enc_p.enc.norm_layers_2.{i}.gamma"])
         put(f"enc.{i}.ln2.b", sd[f"enc_p.enc.norm_layers_2.{i}.beta"])
-    conv("enc_p.proj", sd["enc_p.proj.weight"], sd["enc_p.proj.bias"])
+    conv("enc_p.proj", sd["enc_p.proj.weight"], sd["enc_p.proj.bias"], tc=True)
 
     for fidx in range(cfg["n_flows"]):
         p = f"flow.flows.{2 * fidx}"
         q = f"flow.{fidx}"
-        conv(q + ".pre", sd[p + ".pre.weight"], sd[p + ".pre.bias"])
+        conv(q + ".pre", sd[p + ".pre.weight"], sd[p + ".pre.bias"], tc=True)
         for l in range(cfg["wn_layers"]):
             w = fold_weight_norm(sd, f"{p}.enc.in_layers.{l}")
             b = sd[f"{p}.enc.in_layers.{l}.bias"]
             idx = torch.stack([torch.arange(H), torch.arange(H) + H], 1).reshape(-1)  # (t0,s0,t1,s1,..)
-            conv(f"{q}.in.{l}", w[idx], b[idx])
+            conv(f"{q}.in.{l}", w[idx], b[idx], tc=True)
             conv(f"{q}.rs.{l}", fold_weight_norm(sd, f"{p}.enc.res_skip_layers.{l}"),
-                 sd[f"{p}.enc.res_skip_layers.{l}.bias"])
-        conv(q + ".post", sd[p + ".post.weight"], sd[p + ".post.bias"])
+                 sd[f"{p}.enc.res_skip_layers.{l}.bias"], tc=True)
+        conv(q + ".post", sd[p + ".post.weight"], sd[p + ".post.bias"], tc=True)
         put(q + ".snac.w", sd[p + ".snac.weight"][:, :, 0])
         put(q + ".snac.b", sd[p + ".snac.bias"])
 
@@ -132,7 +161,7 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
     put("dec.adapter.scale.b", sd["dec.adapter.W_scale.bias"])
     put("dec.adapter.bias.w", sd["dec.adapter.W_bias.weight"])
     put("dec.adapter.bias.b", sd["dec.adapter.W_bias.bias"])
-    conv("dec.conv_pre", sd["dec.conv_pre.weight"], sd["dec.conv_pre.bias"])
+    conv("dec.conv_pre", sd["dec.conv_pre.weight"], sd["dec.conv_pre.bias"], tc=True)
     put("dec.merge_w", sd["dec.m_source.merge_w"].reshape(-1))
     put("dec.merge_b", sd["dec.m_source.merge_b"].reshape(-1))
     for i, (rate, k) in enumerate(zip(cfg["up_rates"], cfg["up_kernels"])):
