@@ -16,10 +16,14 @@
 // tile is therefore ONE contiguous run of R*16 bytes = one bulk copy straight into the K-major
 // panel layout of tc.cuh, the zero rows are the conv's zero padding, and every tap is the same
 // tile addressed through a row-shifted descriptor.
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace svcb {
+
+static inline unsigned tc_cols_host(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 constexpr int TC_M = 128;
 constexpr int P8_PAD = 32;
@@ -37,79 +41,115 @@ __device__ __forceinline__ float fast_sin(float x) {
 }
 
 // ------------------------------------------------------------------------------------ snake_pack
+// One CTA = 8 channels (one K-octet) x SP_TL image rows.  Three phases over shared memory:
+//  (a) x rows with a 6-sample halo, replicate-clamped at the sequence ends;
+//  (b) one work item per INPUT sample a: both up-sampled Snake values v[2a], v[2a+1] from the same
+//      7 inputs (12 FMA + 2 SFU sines), stored at vs[j], j = m - (2*n0 - 5);
+//  (c) one thread per pair of output rows: 14 consecutive v (4 x LDS.128) -> two 12-tap
+//      decimations per channel, bf16 hi/lo split, two 16-byte rows stored contiguously.
+// Only the first/last CTA of a sequence needs the replicate padding of v (fix-up pass).
 constexpr int SP_TL = 512;  // image rows per CTA
+constexpr int SP_XW = SP_TL + 12;
+constexpr int SP_VW = 2 * SP_TL + 16;
 
 __global__ void __launch_bounds__(256)
 snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                   const float* __restrict__ ea, const float* __restrict__ inv_b,
                   const float* __restrict__ fu, const float* __restrict__ fd, int C, int L, int Lp) {
   extern __shared__ __align__(16) float sp_smem[];
-  constexpr int XW = SP_TL + 12, VW = 2 * SP_TL + 12;
-  float* xs = sp_smem;            // [8][XW]
-  float* vs = sp_smem + 8 * XW;   // [8][VW]
-  __shared__ float f_up[12], f_dn[12];
+  float* xs = sp_smem;                 // [8][SP_XW]
+  float* vs = sp_smem + 8 * SP_XW;     // [8][SP_VW]
+  __shared__ float f_up[12], f_dn[12], s_ea[8], s_ib[8];
   const int tid = threadIdx.x;
   const int oc = blockIdx.y, b = blockIdx.z;
-  const int row0 = blockIdx.x * SP_TL;      // first image row of this CTA
-  const int n0 = row0 - P8_PAD;             // its sequence position
+  const int row0 = blockIdx.x * SP_TL;  // first image row of this CTA
+  const int n0 = row0 - P8_PAD;         // its sequence position
+  const int nvalid = min(8, C - oc * 8);
   if (tid < 12) { f_up[tid] = __ldg(fu + tid); f_dn[tid] = __ldg(fd + tid); }
-  const long long img = ((long long)b * gridDim.y + oc) * Lp;
-  const bool any = n0 < L && n0 + SP_TL > 0 && oc * 8 < C;  // block-uniform
-  if (any) {
-    const float* xb = x + (long long)b * C * L;
-    for (int idx = tid; idx < 8 * XW; idx += 256) {
-      const int c = idx / XW, i = idx - c * XW;
-      const int cg = oc * 8 + c;
-      int g = n0 - 6 + i;
-      g = min(max(g, 0), L - 1);
-      xs[idx] = cg < C ? __ldg(xb + (long long)cg * L + g) : 0.f;
-    }
-    __syncthreads();
-    constexpr int NV = 2 * SP_TL + 10;
-    for (int idx = tid; idx < 8 * NV; idx += 256) {
-      const int c = idx / NV, iv = idx - c * NV;
-      const int cg = min(oc * 8 + c, C - 1);
-      int m = 2 * n0 - 5 + iv;
-      m = min(max(m, 0), 2 * L - 1);
-      const int a = m >> 1;
-      const float* xp = xs + c * XW + (a - (n0 - 6));
-      float acc = 0.f;
-      if ((m & 1) == 0) {
-#pragma unroll
-        for (int d = -3; d <= 2; ++d) acc = fmaf(xp[d], f_up[5 - 2 * d], acc);
-      } else {
-#pragma unroll
-        for (int d = -2; d <= 3; ++d) acc = fmaf(xp[d], f_up[6 - 2 * d], acc);
-      }
-      const float u = 2.f * acc;
-      const float sn = fast_sin(u * __ldg(ea + cg));
-      vs[c * VW + iv] = u + __ldg(inv_b + cg) * (sn * sn);
-    }
-    __syncthreads();
+  if (tid >= 32 && tid < 32 + 8 && tid - 32 < nvalid) {
+    s_ea[tid - 32] = __ldg(ea + oc * 8 + tid - 32);
+    s_ib[tid - 32] = __ldg(inv_b + oc * 8 + tid - 32);
   }
-  for (int r = tid; r < SP_TL; r += 256) {
-    const int row = row0 + r;
-    if (row >= Lp) break;
-    const int tau = n0 + r;
-    __align__(16) __nv_bfloat16 h8[8], l8[8];
-    const bool inside = any && tau >= 0 && tau < L;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      float o = 0.f;
-      if (inside && oc * 8 + c < C) {
-        const float2* vp = reinterpret_cast<const float2*>(vs + c * VW + 2 * r);
-#pragma unroll
-        for (int k = 0; k < 6; ++k) {
-          const float2 v2 = vp[k];
-          o = fmaf(v2.x, f_dn[2 * k], o);
-          o = fmaf(v2.y, f_dn[2 * k + 1], o);
+  const long long img = ((long long)b * gridDim.y + oc) * Lp;
+  const bool any = n0 < L && n0 + SP_TL > 0 && nvalid > 0;  // block-uniform
+  const int mbase = 2 * n0 - 5;
+  if (any) {
+    const float* xb = x + ((long long)b * C + oc * 8) * L;
+    for (int c = 0; c < nvalid; ++c) {
+      const float* xr = xb + (long long)c * L;
+      for (int i = tid; i < SP_XW; i += 256) {
+        const int g = min(max(n0 - 6 + i, 0), L - 1);
+        xs[c * SP_XW + i] = __ldg(xr + g);
+      }
+    }
+    __syncthreads();
+    for (int c = 0; c < nvalid; ++c) {
+      const float a_ = s_ea[c], ib = s_ib[c];
+      const float* xc = xs + c * SP_XW;
+      float* vc = vs + c * SP_VW;
+      for (int ar = tid - 3; ar <= SP_TL + 2; ar += 256) {   // a - n0
+        const float* xp = xc + ar + 6;
+        const float xm3 = xp[-3], xm2 = xp[-2], xm1 = xp[-1], x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+        float ue = xm3 * f_up[11];
+        ue = fmaf(xm2, f_up[9], ue); ue = fmaf(xm1, f_up[7], ue); ue = fmaf(x0, f_up[5], ue);
+        ue = fmaf(x1, f_up[3], ue); ue = fmaf(x2, f_up[1], ue);
+        float uo = xm2 * f_up[10];
+        uo = fmaf(xm1, f_up[8], uo); uo = fmaf(x0, f_up[6], uo); uo = fmaf(x1, f_up[4], uo);
+        uo = fmaf(x2, f_up[2], uo); uo = fmaf(x3, f_up[0], uo);
+        ue *= 2.f; uo *= 2.f;
+        const float se = fast_sin(ue * a_), so = fast_sin(uo * a_);
+        const int j = 2 * ar + 5;
+        if (j >= 0) vc[j] = fmaf(ib, se * se, ue);
+        vc[j + 1] = fmaf(ib, so * so, uo);
+      }
+    }
+    __syncthreads();
+    if (mbase < 0 || mbase + 2 * SP_TL + 10 > 2 * L) {  // replicate padding of v at the sequence ends
+      const int jlo = -mbase, jhi = 2 * L - 1 - mbase;   // positions of v[0] and v[2L-1]
+      for (int c = 0; c < nvalid; ++c) {
+        float* vc = vs + c * SP_VW;
+        for (int j = tid; j < 2 * SP_TL + 12; j += 256) {
+          if (j < jlo) vc[j] = vc[jlo];
+          else if (j > jhi && jhi >= 0) vc[j] = vc[jhi];
         }
       }
-      h8[c] = __float2bfloat16_rn(o);
-      l8[c] = __float2bfloat16_rn(o - __bfloat162float(h8[c]));
+      __syncthreads();
     }
-    *reinterpret_cast<uint4*>(hi + (img + row) * 8) = *reinterpret_cast<const uint4*>(h8);
-    if (lo) *reinterpret_cast<uint4*>(lo + (img + row) * 8) = *reinterpret_cast<const uint4*>(l8);
+  }
+  // (c) rows 2*tid, 2*tid+1
+  {
+    const int r = 2 * tid;
+    const int row = row0 + r;
+    if (row < Lp) {
+      const int tau = n0 + r;
+      __align__(16) __nv_bfloat16 h8[16], l8[16];  // [row parity][channel]
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float o0 = 0.f, o1 = 0.f;
+        if (any && c < nvalid && tau + 1 >= 0 && tau < L) {
+          const float4* vp = reinterpret_cast<const float4*>(vs + c * SP_VW + 2 * r);
+          const float4 q0 = vp[0], q1 = vp[1], q2 = vp[2], q3 = vp[3];
+          const float w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
+                               q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+#pragma unroll
+          for (int k = 0; k < 12; ++k) { o0 = fmaf(w[k], f_dn[k], o0); o1 = fmaf(w[k + 2], f_dn[k], o1); }
+          if (tau < 0) o0 = 0.f;
+          if (tau + 1 >= L) o1 = 0.f;
+        }
+        h8[c] = __float2bfloat16_rn(o0);
+        l8[c] = __float2bfloat16_rn(o0 - __bfloat162float(h8[c]));
+        h8[8 + c] = __float2bfloat16_rn(o1);
+        l8[8 + c] = __float2bfloat16_rn(o1 - __bfloat162float(h8[8 + c]));
+      }
+      uint4* dh = reinterpret_cast<uint4*>(hi + (img + row) * 8);
+      dh[0] = *reinterpret_cast<const uint4*>(h8);
+      dh[1] = *reinterpret_cast<const uint4*>(h8 + 8);
+      if (lo) {
+        uint4* dl = reinterpret_cast<uint4*>(lo + (img + row) * 8);
+        dl[0] = *reinterpret_cast<const uint4*>(l8);
+        dl[1] = *reinterpret_cast<const uint4*>(l8 + 8);
+      }
+    }
   }
 }
 
@@ -122,7 +162,7 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
                       const float* fd, int B, int C, int L, cudaStream_t s) {
   if (B <= 0 || C <= 0 || L <= 0) return SVCB_OK;
   const int cp = (C + 15) / 16 * 16, Lp = p8_rows_of(L);
-  const size_t smem = (size_t)(8 * (SP_TL + 12) + 8 * (2 * SP_TL + 12)) * sizeof(float);
+  const size_t smem = (size_t)(8 * SP_XW + 8 * SP_VW) * sizeof(float);
   static bool attr = false;
   if (!attr) {
     SVCB_CUDA_CHECK(cudaFuncSetAttribute(snake_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -137,35 +177,44 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 }
 
 // ------------------------------------------------------------------------------------ amp_conv_tc
+// Persistent: each CTA walks tiles (item, 128 samples) with a static stride.  Three roles pipeline
+// across tiles through mbarriers:
+//   producer thread  A image rows of tile i+1 (bulk copies, 1-2 buffers) and the weight tiles
+//                    (all taps resident in shared memory when they fit, else a 2-slot ring per tile)
+//   MMA thread       all taps x split parts of tile i into TMEM accumulator (i & 1)
+//   4 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
+struct AmpPlan { int resident, nabuf, acc_stride, ncols; size_t smem; };
+
 __global__ void __launch_bounds__(192, 1)
-amp_conv_tc_kernel(const AmpConvParams p) {
+amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, const int acc_stride,
+                   const uint32_t ncols) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_a, bar_full[2], bar_empty[2], bar_acc;
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[2], w_empty[2], w_res, t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.y;
-  const int t0 = blockIdx.x * TC_M;
   const int P = p.dil * (p.K - 1) / 2;
   const int R = TC_M + (p.K - 1) * p.dil;
   const int KC = p.Cp / 8;
-  const uint32_t a_bytes = (uint32_t)KC * R * 16u;
-  const uint32_t wb = (uint32_t)p.Cp * p.Cp * 2u;
   const int parts = p.nsplit == 3 ? 2 : 1;
+  const uint32_t a_part = (uint32_t)KC * R * 16u;
+  const uint32_t a_buf = a_part * parts;
+  const uint32_t wb = (uint32_t)p.Cp * p.Cp * 2u;
   const int nch = p.K * parts;
-  uint8_t* A_hi = smem;
-  uint8_t* A_lo = smem + a_bytes;
-  uint8_t* W0 = smem + (uint32_t)parts * a_bytes;
-  uint8_t* W1 = W0 + wb;
+  uint8_t* Abase = smem;
+  uint8_t* Wbase = smem + (size_t)nabuf * a_buf;
+  const int tpi = (p.L + TC_M - 1) / TC_M;
+  const int ntiles = p.B * tpi;
 
   if (tid == 0) {
-    tc::mbar_init(&bar_a, 1);
-    tc::mbar_init(&bar_full[0], 1); tc::mbar_init(&bar_full[1], 1);
-    tc::mbar_init(&bar_empty[0], 1); tc::mbar_init(&bar_empty[1], 1);
-    tc::mbar_init(&bar_acc, 1);
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1);
+      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
+      tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 128);
+    }
+    tc::mbar_init(&w_res, 1);
     tc::fence_barrier_init();
   }
-  const uint32_t ncols = tc::tmem_cols_for(p.Cp);
   __syncwarp();
   if (warp == 4) tc::tmem_alloc(&tmem_slot, ncols);
   tc::fence_before_sync();
@@ -174,74 +223,110 @@ amp_conv_tc_kernel(const AmpConvParams p) {
   const uint32_t tmem = tmem_slot;
 
   if (tid == 128) {
-    // ---------------------------------------------------------------- producer: A image rows + weight ring
-    const uint32_t run = (uint32_t)R * 16u;
-    tc::mbar_arrive_expect_tx(&bar_a, run * KC * parts);
-    const long long row = P8_PAD + t0 - P;
-    for (int part = 0; part < parts; ++part) {
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(part == 0 ? p.a_hi : p.a_lo);
-      uint8_t* dst = part == 0 ? A_hi : A_lo;
-      for (int kc = 0; kc < KC; ++kc)
-        tc::bulk_g2s(dst + (size_t)kc * run, src + (((long long)b * KC + kc) * p.Lp + row) * 16, run, &bar_a);
+    // ---------------------------------------------------------------- producer
+    if (resident) {
+      tc::mbar_arrive_expect_tx(&w_res, wb * (uint32_t)nch);
+      for (int i = 0; i < nch; ++i)
+        tc::bulk_g2s(Wbase + (size_t)i * wb, p.wpk + ((size_t)(i / parts) * 2 + (i % parts)) * wb, wb, &w_res);
     }
-    for (int i = 0; i < nch; ++i) {
-      const int st = i & 1;
-      if (i >= 2) tc::mbar_wait(&bar_empty[st], (uint32_t)(((i >> 1) - 1) & 1));
-      tc::mbar_arrive_expect_tx(&bar_full[st], wb);
-      const int tap = i / parts, part = i % parts;
-      tc::bulk_g2s(st ? W1 : W0, p.wpk + ((size_t)tap * 2 + part) * wb, wb, &bar_full[st]);
+    const uint32_t run = (uint32_t)R * 16u;
+    int it = 0, wi = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it % nabuf;
+      if (it >= nabuf) tc::mbar_wait(&a_empty[buf], (uint32_t)(((it / nabuf) - 1) & 1));
+      const int b = tile / tpi, t0 = (tile - b * tpi) * TC_M;
+      tc::mbar_arrive_expect_tx(&a_full[buf], run * KC * parts);
+      const long long row = P8_PAD + t0 - P;
+      for (int part = 0; part < parts; ++part) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(part == 0 ? p.a_hi : p.a_lo);
+        uint8_t* dst = Abase + (size_t)buf * a_buf + (size_t)part * a_part;
+        for (int kc = 0; kc < KC; ++kc)
+          tc::bulk_g2s(dst + (size_t)kc * run, src + (((long long)b * KC + kc) * p.Lp + row) * 16, run, &a_full[buf]);
+      }
+      if (!resident) {
+        for (int i = 0; i < nch; ++i, ++wi) {
+          const int st = wi & 1;
+          if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          tc::mbar_arrive_expect_tx(&w_full[st], wb);
+          tc::bulk_g2s(Wbase + (size_t)st * wb, p.wpk + ((size_t)(i / parts) * 2 + (i % parts)) * wb, wb, &w_full[st]);
+        }
+      }
     }
   } else if (tid == 160) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = tc::idesc_bf16(TC_M, p.Cp);
-    const uint32_t a_hi = tc::smem_u32(A_hi), a_lo = tc::smem_u32(A_lo);
-    const uint32_t w_addr[2] = {tc::smem_u32(W0), tc::smem_u32(W1)};
+    const uint32_t a0 = tc::smem_u32(Abase), w0 = tc::smem_u32(Wbase);
     const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.Cp * 16u;
-    uint32_t accumulate = 0;
-    tc::mbar_wait(&bar_a, 0);
-    for (int i = 0; i < nch; ++i) {
-      const int st = i & 1;
-      tc::mbar_wait(&bar_full[st], (uint32_t)((i >> 1) & 1));
+    if (resident) tc::mbar_wait(&w_res, 0);
+    int it = 0, wi = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int buf = it % nabuf, acc = it & 1;
+      tc::mbar_wait(&a_full[buf], (uint32_t)((it / nabuf) & 1));
+      if (it >= 2) tc::mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) - 1) & 1));
       tc::fence_after_sync();
-      const int tap = i / parts, part = i % parts;
-      const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
-      const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
-      for (int ap = 0; ap < n_a; ++ap) {
-        const uint32_t abase = (ap == 0 ? a_hi : a_lo) + row_off;
-        for (int kk = 0; kk < p.Cp / 16; ++kk) {
-          const uint64_t ad = tc::smem_desc(abase + (uint32_t)kk * 2u * lbo_a, lbo_a);
-          const uint64_t bd = tc::smem_desc(w_addr[st] + (uint32_t)kk * 2u * lbo_b, lbo_b);
-          tc::mma_bf16(tmem, ad, bd, idesc, accumulate);
-          accumulate = 1;
+      const uint32_t d_tmem = tmem + (uint32_t)(acc * acc_stride);
+      const uint32_t a_hi = a0 + (uint32_t)buf * a_buf, a_lo = a_hi + a_part;
+      uint32_t accumulate = 0;
+      for (int i = 0; i < nch; ++i) {
+        uint32_t wbase;
+        int st = 0;
+        if (resident) {
+          wbase = w0 + (uint32_t)i * wb;
+        } else {
+          st = wi & 1;
+          tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+          tc::fence_after_sync();
+          wbase = w0 + (uint32_t)st * wb;
         }
+        const int tap = i / parts, part = i % parts;
+        const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
+        const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
+        for (int ap = 0; ap < n_a; ++ap) {
+          const uint32_t abase = (ap == 0 ? a_hi : a_lo) + row_off;
+          for (int kk = 0; kk < p.Cp / 16; ++kk) {
+            const uint64_t ad = tc::smem_desc(abase + (uint32_t)kk * 2u * lbo_a, lbo_a);
+            const uint64_t bd = tc::smem_desc(wbase + (uint32_t)kk * 2u * lbo_b, lbo_b);
+            tc::mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+            accumulate = 1;
+          }
+        }
+        if (!resident) { tc::mma_commit(&w_empty[st]); ++wi; }
       }
-      tc::mma_commit(&bar_empty[st]);
+      tc::mma_commit(&a_empty[buf]);
+      tc::mma_commit(&t_full[acc]);
     }
-    tc::mma_commit(&bar_acc);
   } else if (warp < 4) {
     // ---------------------------------------------------------------- epilogue (TMEM lanes 32w..32w+31)
-    tc::mbar_wait(&bar_acc, 0);
-    tc::fence_after_sync();
-    const int t = t0 + warp * 32 + lane;
-    const long long rowb = (long long)b * p.C * p.L;
-    for (int c0 = 0; c0 < p.Cp; c0 += 16) {
-      uint32_t v[16];
-      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      if (t < p.L) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      tc::mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      tc::fence_after_sync();
+      const int b = tile / tpi, t0 = (tile - b * tpi) * TC_M;
+      const int t = t0 + warp * 32 + lane;
+      const long long rowb = (long long)b * p.C * p.L;
+      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_stride);
+      for (int c0 = 0; c0 < p.Cp; c0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(tbase + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (t < p.L) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int co = c0 + j;
-          if (co < p.C) {
-            const long long off = rowb + (long long)co * p.L + t;
-            float o = __uint_as_float(v[j]) + __ldg(p.bias + co);
-            if (p.res) o += p.res[off];
-            if (p.accum) o += p.y[off];
-            if (p.out_div != 0.f) o = o / p.out_div;
-            p.y[off] = o;
+          for (int j = 0; j < 16; ++j) {
+            const int co = c0 + j;
+            if (co < p.C) {
+              const long long off = rowb + (long long)co * p.L + t;
+              float o = __uint_as_float(v[j]) + __ldg(p.bias + co);
+              if (p.res) o += p.res[off];
+              if (p.accum) o += p.y[off];
+              if (p.out_div != 0.f) o = o / p.out_div;
+              p.y[off] = o;
+            }
           }
         }
       }
+      tc::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&t_empty[acc])) : "memory");
     }
   }
   tc::fence_before_sync();
@@ -249,11 +334,23 @@ amp_conv_tc_kernel(const AmpConvParams p) {
   if (warp == 4) tc::tmem_dealloc(tmem, ncols);
 }
 
-size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit) {
+static AmpPlan amp_plan(int Cp, int K, int dil, int nsplit) {
   const int R = TC_M + (K - 1) * dil;
-  const size_t a = (size_t)(Cp / 8) * R * 16 * (nsplit == 3 ? 2 : 1);
-  return a + 2 * (size_t)Cp * Cp * 2 + 128;
+  const int parts = nsplit == 3 ? 2 : 1;
+  const size_t a_buf = (size_t)(Cp / 8) * R * 16 * parts;
+  const size_t wb = (size_t)Cp * Cp * 2;
+  const size_t nch = (size_t)K * parts;
+  const size_t limit = 227 * 1024 - 1024;
+  AmpPlan pl;
+  pl.acc_stride = (Cp + 31) / 32 * 32;
+  pl.ncols = (int)tc_cols_host(2 * pl.acc_stride);
+  if (2 * a_buf + nch * wb + 128 <= limit) { pl.resident = 1; pl.nabuf = 2; pl.smem = 2 * a_buf + nch * wb + 128; }
+  else if (2 * a_buf + 2 * wb + 128 <= limit) { pl.resident = 0; pl.nabuf = 2; pl.smem = 2 * a_buf + 2 * wb + 128; }
+  else { pl.resident = 0; pl.nabuf = 1; pl.smem = a_buf + 2 * wb + 128; }
+  return pl;
 }
+
+size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit) { return amp_plan(Cp, K, dil, nsplit).smem; }
 
 int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
   if (p.Cp % 16 || p.Cp < 16 || p.Cp > 256 || p.Cp < p.C || (p.nsplit != 1 && p.nsplit != 3)) {
@@ -264,19 +361,29 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
     set_error("amp_conv_tc: operand image does not match (halo > 32 rows or wrong Lp)");
     return SVCB_E_BAD_SHAPE;
   }
-  const size_t smem = amp_conv_tc_smem_bytes(p.Cp, p.K, p.dil, p.nsplit);
-  if (smem > 227 * 1024 - 512) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
+  const AmpPlan pl = amp_plan(p.Cp, p.K, p.dil, p.nsplit);
+  if (pl.smem > 227 * 1024 - 512) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;  // the dynamic limit excludes the kernel's (small) static shared memory
-  if (smem > attr_bytes) {
+  static int n_sm = 0;
+  if (pl.smem > attr_bytes) {
     SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
-    attr_bytes = smem;
+                                         (int)pl.smem));
+    attr_bytes = pl.smem;
   }
-  dim3 grid((p.L + TC_M - 1) / TC_M, p.B);
+  if (!n_sm) {
+    int dev = 0;
+    SVCB_CUDA_CHECK(cudaGetDevice(&dev));
+    SVCB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int occ = 1;
+  SVCB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, amp_conv_tc_kernel, 192, pl.smem));
+  occ = std::max(1, std::min(occ, 512 / pl.ncols));
+  const int ntiles = p.B * ((p.L + TC_M - 1) / TC_M);
+  const int grid = std::min(ntiles, n_sm * occ);
   const double macs = (double)p.B * p.L * p.C * p.C * p.K;
   KernelScope ks(p.nsplit == 3 ? "amp_conv_tc_bf16x3" : "amp_conv_tc_bf16", s, 2.0 * macs,
                  (double)p.B * p.C * p.L * ((p.nsplit == 3 ? 4.0 : 2.0) + 4.0 * (p.res ? 2 : 1)));
-  amp_conv_tc_kernel<<<grid, 192, smem, s>>>(p);
+  amp_conv_tc_kernel<<<grid, 192, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols);
   SVCB_LAUNCH_CHECK("amp_conv_tc");
   return SVCB_OK;
 }
