@@ -18,10 +18,11 @@ WAVE_TOL = 1e-3      # the stated gate
 TIGHT = 2e-4         # what fp32 kernels are expected to meet
 
 
-def _model(hp, sd):
+def _model(hp, sd, precision=0):
     from whisper_vits_svc_b200 import models
     assert torch.cuda.is_available()
-    m = models.SynthesizerInfer(hp.data.filter_length // 2 + 1, hp.data.segment_size // hp.data.hop_length, hp)
+    m = models.SynthesizerInfer(hp.data.filter_length // 2 + 1, hp.data.segment_size // hp.data.hop_length, hp,
+                                precision=precision)
     m.load_state_dict(sd)
     m.eval()
     return m.to("cuda")
@@ -29,7 +30,8 @@ def _model(hp, sd):
 
 @pytest.fixture(scope="module")
 def model(hp, sd):
-    return _model(hp, sd)
+    """precision 0: every conv on the fp32 CUDA-core kernels (tightest parity, 1e-6)."""
+    return _model(hp, sd, 0)
 
 
 @pytest.mark.parametrize("name", ["infer_b2_t48", "infer_b3_t70_ragged"])
@@ -167,3 +169,37 @@ def test_tensor_core_generator_modes(hp, sd, precision, tol):
     err = max_abs(wave, wave_o)
     print(f"precision={precision}: wave max-abs {err:.3e}")
     assert err <= tol
+
+
+@pytest.fixture(scope="module")
+def model_tc(hp, sd):
+    from whisper_vits_svc_b200 import models
+    m = models.SynthesizerInfer(513, 25, hp, precision=3)
+    m.load_state_dict(sd)
+    return m.to("cuda")
+
+
+@pytest.mark.parametrize("name", ["infer_b2_t48", "infer_b3_t70_ragged"])
+def test_golden_full_tensor_core_mode(model_tc, hp, name):
+    """The default (bf16x3 tensor-core + fused narrow-stage) mode against the reference's golden
+    waveforms: the 1e-3 gate with margin."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    d = make_inputs(int(g["seed"]), int(g["B"]), int(g["T"]), hp, ragged=bool(g["ragged"]))
+    wave = model_tc.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], torch.from_numpy(g["source"]),
+                              eps=d["eps"])
+    err = max_abs(wave, g["wave"])
+    print(f"{name} (precision 3): wave max-abs err {err:.3e}")
+    assert err <= 2e-4
+
+
+def test_full_size_tensor_core_mode(model_tc, hp, sd):
+    """10 s items (tiles of every stage interior + both sequence edges) in the default mode."""
+    B, T = 2, 1000
+    d = make_inputs(31, B, T, hp)
+    src = O.pitch2source(sd, hp, d["pit"], d["rand_ini"], d["noise"])
+    wave = model_tc.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, eps=d["eps"])
+    wave_o = O.synthesizer_infer(sd, hp, d["ppg"][:1], d["vec"][:1], d["pit"][:1], d["spk"][:1], d["ppg_l"][:1],
+                                 src[:1], d["eps"][:1])
+    err = max_abs(wave[:1], wave_o)
+    print(f"10 s item (precision 3): wave max-abs err {err:.3e}")
+    assert torch.isfinite(wave).all() and err <= 2e-4

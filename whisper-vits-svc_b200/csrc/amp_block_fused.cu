@@ -1,0 +1,264 @@
+// Whole AMP block fused in shared memory — for the narrow generator stages (C = 20, 10).
+//
+// Replaces one AMPBlock.forward (vits_decoder/bigv.py:50-58): three units of
+//   x = x + conv2(SnakeAlias(conv1_d(SnakeAlias(x))))                d = 1, 3, 5
+// i.e. 6 Conv1d + 6 SnakeAlias (vits_decoder/alias/act.py:124-128) + 3 residual adds, plus the
+// stage-mean bookkeeping of generator.py:188-194, in ONE kernel: x is read once, the result is
+// written once (SURVEY.md §8a row a9 "per-block fused kernel", row a10).
+//
+// Why CUDA cores here: with C = 10 / 20 a tcgen05 MMA has N = 16 / 32 and costs as much issue time
+// as a full-width one (measured: these two stages took 75 of 107 ms of the tensor-core AMP path
+// while holding 20 % of its FLOPs — profiles/r01_notes.md); their arithmetic intensity unfused is
+// ~45-330 FLOP/B (fp32-FMA side of the ridge).  Fused, the stage is bound by fp32 FMA issue and
+// exact fp32 — no operand splitting.
+//
+// One CTA = (item, TOUT output samples) with a halo H = sum over units of the receptive field
+// (6 + d(K-1)/2 + 6 + (K-1)/2).  Three [C][W] buffers live in shared memory (X residual stream,
+// Y, Z) with zeroed guard bands so the convolutions need no bounds checks; positions outside the
+// sequence are kept at zero (= the convs' zero padding) and SnakeAlias clamps its taps to the
+// sequence (= its replicate padding), so tile edges reproduce the reference exactly.
+#include <cstdio>
+
+#include "common.cuh"
+
+namespace svcb {
+
+constexpr int AB_THREADS = 512;
+constexpr int AB_GUARD = 32;   // zeroed floats on both sides of every row (>= max conv reach 25)
+
+__host__ __device__ inline int ab_halo(int K, const int* dil) {
+  int h = 0;
+  for (int d = 0; d < 3; ++d) h += 6 + dil[d] * (K - 1) / 2 + 6 + (K - 1) / 2;
+  return h;
+}
+
+template <int C>
+struct AbCfg {
+  static constexpr int CP = (C + 3) / 4 * 4;
+  static constexpr int TOUT = C <= 10 ? 1024 : 512;
+};
+
+// SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
+// index inside the sequence.  Warp-private: a warp takes (channel, 64-output chunk) items, builds the
+// 2x-rate Snake values of its chunk in its own scratch slice and decimates them — only __syncwarp,
+// no CTA barrier inside the activation.
+constexpr int AB_CH = 64;
+constexpr int AB_VSL = 2 * (AB_CH + 6) + 4;  // scratch floats per warp
+
+template <int C>
+__device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst, float* V,
+                                         const float* f_up, const float* f_dn, const float* ea,
+                                         const float* ib, int W, int WS, int lo_i, int hi_i, int tid) {
+  const int warp = tid >> 5, lane = tid & 31;
+  float* vw = V + warp * AB_VSL;
+  const int nchunks = (W + AB_CH - 1) / AB_CH;
+  const int mlo = 2 * lo_i, mhi = 2 * hi_i + 1;
+  float fu[12], fdn[12];
+#pragma unroll
+  for (int k = 0; k < 12; ++k) { fu[k] = f_up[k]; fdn[k] = f_dn[k]; }
+  for (int item = warp; item < C * nchunks; item += AB_THREADS / 32) {
+    const int c = item / nchunks, n0 = (item - c * nchunks) * AB_CH;
+    const float* xr = src + c * WS + AB_GUARD;
+    const float a_ = ea[c], b_ = ib[c];
+    for (int ai = lane; ai < AB_CH + 6; ai += 32) {
+      const int a = n0 - 3 + ai;
+      float x[7];
+      if (a - 3 >= lo_i && a + 3 <= hi_i) {
+#pragma unroll
+        for (int d = 0; d < 7; ++d) x[d] = xr[a - 3 + d];
+      } else {
+#pragma unroll
+        for (int d = 0; d < 7; ++d) x[d] = xr[min(max(a - 3 + d, lo_i), hi_i)];
+      }
+      float ue = x[0] * fu[11];
+      ue = fmaf(x[1], fu[9], ue); ue = fmaf(x[2], fu[7], ue); ue = fmaf(x[3], fu[5], ue);
+      ue = fmaf(x[4], fu[3], ue); ue = fmaf(x[5], fu[1], ue);
+      float uo = x[1] * fu[10];
+      uo = fmaf(x[2], fu[8], uo); uo = fmaf(x[3], fu[6], uo); uo = fmaf(x[4], fu[4], uo);
+      uo = fmaf(x[5], fu[2], uo); uo = fmaf(x[6], fu[0], uo);
+      ue *= 2.f; uo *= 2.f;
+      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
+      vw[2 * ai] = fmaf(b_, se * se, ue);        // v[2a]   at j = m - 2*(n0-3)
+      vw[2 * ai + 1] = fmaf(b_, so * so, uo);    // v[2a+1]
+    }
+    __syncwarp();
+    const int jbase = 2 * (n0 - 3);
+    for (int ni = lane; ni < AB_CH; ni += 32) {
+      const int n = n0 + ni;
+      if (n >= W) break;
+      float o = 0.f;
+      if (n >= lo_i && n <= hi_i) {
+        const int m0 = 2 * n - 5;
+        if (m0 >= mlo && m0 + 11 <= mhi) {
+          const float* vp = vw + (m0 - jbase);
+#pragma unroll
+          for (int k = 0; k < 12; ++k) o = fmaf(vp[k], fdn[k], o);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 12; ++k) o = fmaf(vw[min(max(m0 + k, mlo), mhi) - jbase], fdn[k], o);
+        }
+      }
+      dst[c * WS + AB_GUARD + n] = o;  // zero outside the sequence = zero padding of the next conv
+    }
+    __syncwarp();
+  }
+}
+
+// dst[co][t] = bias[co] + sum_ci sum_j w[ci][j][co] * src[ci][t + j*dil - P]  (+ dst[co][t] if RES);
+// a thread owns two time steps (t, t + AB_THREADS) so every weight vector load feeds 2*C FMAs.
+template <int C, bool RES>
+__device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __restrict__ dst,
+                                        const float* __restrict__ wsm, const float* __restrict__ bsm,
+                                        int K, int dil, int W, int WS, int lo_i, int hi_i, int tid) {
+  constexpr int CP = AbCfg<C>::CP;
+  const int P = dil * (K - 1) / 2;
+  for (int tb = tid; tb < W; tb += 2 * AB_THREADS) {
+    const int t1 = tb + AB_THREADS;
+    const bool two = t1 < W;
+    float acc0[CP], acc1[CP];
+#pragma unroll
+    for (int co = 0; co < CP; ++co) { acc0[co] = co < C ? bsm[co] : 0.f; acc1[co] = acc0[co]; }
+    const float* sp0 = src + AB_GUARD + tb - P;
+    const float* sp1 = src + AB_GUARD + (two ? t1 : tb) - P;
+    for (int ci = 0; ci < C; ++ci) {
+      const float* s0 = sp0 + ci * WS;
+      const float* s1 = sp1 + ci * WS;
+      const float* wr = wsm + ci * K * CP;
+      for (int j = 0; j < K; ++j) {
+        const float x0 = s0[j * dil], x1 = s1[j * dil];
+        const float4* w4 = reinterpret_cast<const float4*>(wr + j * CP);
+#pragma unroll
+        for (int q = 0; q < CP / 4; ++q) {
+          const float4 w = w4[q];
+          acc0[4 * q + 0] = fmaf(x0, w.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(x1, w.x, acc1[4 * q + 0]);
+          acc0[4 * q + 1] = fmaf(x0, w.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(x1, w.y, acc1[4 * q + 1]);
+          acc0[4 * q + 2] = fmaf(x0, w.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(x1, w.z, acc1[4 * q + 2]);
+          acc0[4 * q + 3] = fmaf(x0, w.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(x1, w.w, acc1[4 * q + 3]);
+        }
+      }
+    }
+    const bool in0 = tb >= lo_i && tb <= hi_i, in1 = two && t1 >= lo_i && t1 <= hi_i;
+#pragma unroll
+    for (int co = 0; co < C; ++co) {
+      float* d0 = dst + co * WS + AB_GUARD + tb;
+      float o0 = acc0[co];
+      if (RES) o0 += *d0;
+      *d0 = in0 ? o0 : 0.f;
+      if (two) {
+        float* d1 = dst + co * WS + AB_GUARD + t1;
+        float o1 = acc1[co];
+        if (RES) o1 += *d1;
+        *d1 = in1 ? o1 : 0.f;
+      }
+    }
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(AB_THREADS, 1)
+amp_block_fused_kernel(const AmpBlockParams p) {
+  constexpr int CP = AbCfg<C>::CP;
+  constexpr int TOUT = AbCfg<C>::TOUT;
+  extern __shared__ __align__(16) float ab_smem[];
+  __shared__ float f_up[12], f_dn[12], s_ea[C], s_ib[C], s_bias[CP];
+  const int tid = threadIdx.x;
+  const int b = blockIdx.y;
+  const int t0 = blockIdx.x * TOUT;
+  const int K = p.K;
+  const int H = ab_halo(K, p.dil);
+  const int W = TOUT + 2 * H;
+  const int WS = W + 2 * AB_GUARD;
+  float* X = ab_smem;
+  float* Y = X + C * WS;
+  float* Z = Y + C * WS;
+  float* V = Z + C * WS;                       // per-warp Snake scratch
+  float* wsm = V + (AB_THREADS / 32) * AB_VSL; // [C][K][CP]
+  const int base = t0 - H;                     // sequence position of buffer index 0
+  const int lo_i = max(0, -base), hi_i = min(W - 1, p.L - 1 - base);
+
+  // zero everything once (guard bands must stay zero), then load x
+  for (int i = tid; i < 3 * C * WS; i += AB_THREADS) X[i] = 0.f;
+  __syncthreads();
+  const float* xb = p.x + (long long)b * C * p.L;
+  for (int i = tid; i < C * W; i += AB_THREADS) {
+    const int c = i / W, n = i - c * W;
+    if (n >= lo_i && n <= hi_i) X[c * WS + AB_GUARD + n] = __ldg(xb + (long long)c * p.L + base + n);
+  }
+  __syncthreads();
+
+  for (int d = 0; d < 3; ++d) {
+    for (int half = 0; half < 2; ++half) {
+      const int a = 2 * d + half;
+      // stage this link's parameters: Snake a, conv (half == 0 ? c1[d] : c2[d])
+      if (tid < 12) { f_up[tid] = __ldg(p.fu[a] + tid); f_dn[tid] = __ldg(p.fd[a] + tid); }
+      if (tid >= 32 && tid < 32 + C) { s_ea[tid - 32] = __ldg(p.ea[a] + tid - 32); s_ib[tid - 32] = __ldg(p.ib[a] + tid - 32); }
+      const float* wg = half == 0 ? p.w1[d] : p.w2[d];
+      const float* bg = half == 0 ? p.b1[d] : p.b2[d];
+      if (tid >= 64 && tid < 64 + CP) s_bias[tid - 64] = (tid - 64 < C) ? __ldg(bg + tid - 64) : 0.f;
+      for (int i = tid; i < C * K * CP; i += AB_THREADS) {
+        // packed global layout [ci][j][CoutPad8] -> [ci][j][CP]
+        const int co = i % CP, cj = i / CP;
+        wsm[i] = co < p.cout_pad ? __ldg(wg + (long long)cj * p.cout_pad + co) : 0.f;
+      }
+      __syncthreads();
+      if (half == 0) {
+        ab_snake<C>(X, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
+        __syncthreads();
+        ab_conv<C, false>(Y, Z, wsm, s_bias, K, p.dil[d], W, WS, lo_i, hi_i, tid);
+      } else {
+        ab_snake<C>(Z, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
+        __syncthreads();
+        ab_conv<C, true>(Y, X, wsm, s_bias, K, 1, W, WS, lo_i, hi_i, tid);
+      }
+      __syncthreads();
+    }
+  }
+  // write the exact region, folding the stage mean (generator.py:188-194)
+  float* yb = p.y + (long long)b * C * p.L;
+  for (int i = tid; i < C * TOUT; i += AB_THREADS) {
+    const int c = i / TOUT, n = i - c * TOUT;
+    const int t = t0 + n;
+    if (t < p.L) {
+      float o = X[c * WS + AB_GUARD + H + n];
+      const long long off = (long long)c * p.L + t;
+      if (p.accum) o += yb[off];
+      if (p.out_div != 0.f) o = o / p.out_div;
+      yb[off] = o;
+    }
+  }
+}
+
+template <int C>
+static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
+  const int H = ab_halo(p.K, p.dil);
+  const int W = AbCfg<C>::TOUT + 2 * H, WS = W + 2 * AB_GUARD;
+  const size_t smem = ((size_t)3 * C * WS + (AB_THREADS / 32) * AB_VSL + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
+  if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
+  static size_t attr_bytes = 0;
+  if (smem > attr_bytes) {
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_bytes = smem;
+  }
+  dim3 grid((p.L + AbCfg<C>::TOUT - 1) / AbCfg<C>::TOUT, p.B);
+  char kname[64];
+  snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);
+  KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B + 6 * 70.0 * C * (double)p.L * p.B,
+                 (p.accum ? 12.0 : 8.0) * C * (double)p.L * p.B);
+  amp_block_fused_kernel<C><<<grid, AB_THREADS, smem, s>>>(p);
+  SVCB_LAUNCH_CHECK("amp_block_fused");
+  return SVCB_OK;
+}
+
+bool amp_block_fused_supported(int C, int K, const int* dil) {
+  if (C != 10 && C != 20) return false;
+  for (int d = 0; d < 3; ++d) if (dil[d] * (K - 1) / 2 > AB_GUARD) return false;
+  return true;
+}
+
+int launch_amp_block_fused(const AmpBlockParams& p, cudaStream_t s) {
+  if (p.B <= 0 || p.L <= 0) return SVCB_OK;
+  if (!amp_block_fused_supported(p.C, p.K, p.dil)) { set_error("amp_block_fused: unsupported channel count / reach"); return SVCB_E_UNSUPPORTED; }
+  return p.C == 10 ? launch_ab<10>(p, s) : launch_ab<20>(p, s);
+}
+
+}  // namespace svcb

@@ -17,6 +17,7 @@
 // panel layout of tc.cuh, the zero rows are the conv's zero padding, and every tap is the same
 // tile addressed through a row-shifted descriptor.
 #include <algorithm>
+#include <cstdio>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -97,7 +98,7 @@ snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
         uo = fmaf(xm1, f_up[8], uo); uo = fmaf(x0, f_up[6], uo); uo = fmaf(x1, f_up[4], uo);
         uo = fmaf(x2, f_up[2], uo); uo = fmaf(x3, f_up[0], uo);
         ue *= 2.f; uo *= 2.f;
-        const float se = fast_sin(ue * a_), so = fast_sin(uo * a_);
+        const float se = __sinf(ue * a_), so = __sinf(uo * a_);
         const int j = 2 * ar + 5;
         if (j >= 0) vc[j] = fmaf(ib, se * se, ue);
         vc[j + 1] = fmaf(ib, so * so, uo);
@@ -122,7 +123,8 @@ snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
     const int row = row0 + r;
     if (row < Lp) {
       const int tau = n0 + r;
-      __align__(16) __nv_bfloat16 h8[16], l8[16];  // [row parity][channel]
+      __align__(16) __nv_bfloat162 h2[8], l2[8];  // [row parity*4 + channel pair]
+      float prev0 = 0.f, prev1 = 0.f;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         float o0 = 0.f, o1 = 0.f;
@@ -136,18 +138,25 @@ snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
           if (tau < 0) o0 = 0.f;
           if (tau + 1 >= L) o1 = 0.f;
         }
-        h8[c] = __float2bfloat16_rn(o0);
-        l8[c] = __float2bfloat16_rn(o0 - __bfloat162float(h8[c]));
-        h8[8 + c] = __float2bfloat16_rn(o1);
-        l8[8 + c] = __float2bfloat16_rn(o1 - __bfloat162float(h8[8 + c]));
+        if (c & 1) {  // one packed conversion per channel pair and row
+          const __nv_bfloat162 ha = __floats2bfloat162_rn(prev0, o0), hb = __floats2bfloat162_rn(prev1, o1);
+          const float2 fa = __bfloat1622float2(ha), fb = __bfloat1622float2(hb);
+          h2[c >> 1] = ha; h2[4 + (c >> 1)] = hb;
+          l2[c >> 1] = __floats2bfloat162_rn(prev0 - fa.x, o0 - fa.y);
+          l2[4 + (c >> 1)] = __floats2bfloat162_rn(prev1 - fb.x, o1 - fb.y);
+        } else {
+          prev0 = o0; prev1 = o1;
+        }
       }
+      const __nv_bfloat162* h8 = h2;
+      const __nv_bfloat162* l8 = l2;
       uint4* dh = reinterpret_cast<uint4*>(hi + (img + row) * 8);
       dh[0] = *reinterpret_cast<const uint4*>(h8);
-      dh[1] = *reinterpret_cast<const uint4*>(h8 + 8);
+      dh[1] = *reinterpret_cast<const uint4*>(h8 + 4);
       if (lo) {
         uint4* dl = reinterpret_cast<uint4*>(lo + (img + row) * 8);
         dl[0] = *reinterpret_cast<const uint4*>(l8);
-        dl[1] = *reinterpret_cast<const uint4*>(l8 + 8);
+        dl[1] = *reinterpret_cast<const uint4*>(l8 + 4);
       }
     }
   }
@@ -169,7 +178,9 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
     attr = true;
   }
   dim3 grid((Lp + SP_TL - 1) / SP_TL, cp / 8, B);
-  KernelScope ks("snake_pack", s, 70.0 * B * C * (double)L, (lo ? 8.0 : 6.0) * B * C * (double)L);
+  char kname[64];
+  snprintf(kname, sizeof(kname), "snake_pack_c%d", C);
+  KernelScope ks(kname, s, 70.0 * B * C * (double)L, (lo ? 8.0 : 6.0) * B * C * (double)L);
   snake_pack_kernel<<<grid, 256, smem, s>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ea,
                                             inv_b, fu, fd, C, L, Lp);
   SVCB_LAUNCH_CHECK("snake_pack");
@@ -185,7 +196,7 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 //   4 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
 struct AmpPlan { int resident, nabuf, acc_stride, ncols; size_t smem; };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, const int acc_stride,
                    const uint32_t ncols) {
   extern __shared__ __align__(128) uint8_t smem[];
@@ -210,19 +221,19 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1);
       tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
-      tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 128);
+      tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 256);
     }
     tc::mbar_init(&w_res, 1);
     tc::fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 4) tc::tmem_alloc(&tmem_slot, ncols);
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, ncols);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (tid == 128) {
+  if (tid == 256) {
     // ---------------------------------------------------------------- producer
     if (resident) {
       tc::mbar_arrive_expect_tx(&w_res, wb * (uint32_t)nch);
@@ -252,7 +263,7 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
         }
       }
     }
-  } else if (tid == 160) {
+  } else if (tid == 288) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = tc::idesc_bf16(TC_M, p.Cp);
     const uint32_t a0 = tc::smem_u32(Abase), w0 = tc::smem_u32(Wbase);
@@ -266,64 +277,94 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem + (uint32_t)(acc * acc_stride);
       const uint32_t a_hi = a0 + (uint32_t)buf * a_buf, a_lo = a_hi + a_part;
+      // descriptors differ only in the start-address field (units of 16 B): advance by addition
+      const uint64_t ad_hi0 = tc::smem_desc(a_hi, lbo_a), ad_lo0 = tc::smem_desc(a_lo, lbo_a);
+      const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;
+      const int nk = p.Cp / 16;
       uint32_t accumulate = 0;
-      for (int i = 0; i < nch; ++i) {
-        uint32_t wbase;
-        int st = 0;
-        if (resident) {
-          wbase = w0 + (uint32_t)i * wb;
-        } else {
-          st = wi & 1;
-          tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
-          tc::fence_after_sync();
-          wbase = w0 + (uint32_t)st * wb;
-        }
-        const int tap = i / parts, part = i % parts;
-        const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
-        const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
-        for (int ap = 0; ap < n_a; ++ap) {
-          const uint32_t abase = (ap == 0 ? a_hi : a_lo) + row_off;
-          for (int kk = 0; kk < p.Cp / 16; ++kk) {
-            const uint64_t ad = tc::smem_desc(abase + (uint32_t)kk * 2u * lbo_a, lbo_a);
-            const uint64_t bd = tc::smem_desc(wbase + (uint32_t)kk * 2u * lbo_b, lbo_b);
-            tc::mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-            accumulate = 1;
+      int i = 0;
+      for (int tap = 0; tap < p.K; ++tap) {
+        const uint32_t tap_off = (uint32_t)(tap * p.dil);  // rows -> 16-byte units
+        for (int part = 0; part < parts; ++part, ++i) {
+          uint32_t wbase;
+          int st = 0;
+          if (resident) {
+            wbase = w0 + (uint32_t)i * wb;
+          } else {
+            st = wi & 1;
+            tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+            tc::fence_after_sync();
+            wbase = w0 + (uint32_t)st * wb;
           }
+          const uint64_t bd0 = tc::smem_desc(wbase, lbo_b);
+          const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
+          for (int ap = 0; ap < n_a; ++ap) {
+            uint64_t ad = (ap == 0 ? ad_hi0 : ad_lo0) + tap_off;
+            uint64_t bd = bd0;
+            for (int kk = 0; kk < nk; ++kk) {
+              tc::mma_bf16(d_tmem, ad, bd, idesc, accumulate);
+              accumulate = 1;
+              ad += kstep_a;
+              bd += kstep_b;
+            }
+          }
+          if (!resident) { tc::mma_commit(&w_empty[st]); ++wi; }
         }
-        if (!resident) { tc::mma_commit(&w_empty[st]); ++wi; }
       }
       tc::mma_commit(&a_empty[buf]);
       tc::mma_commit(&t_full[acc]);
     }
-  } else if (warp < 4) {
-    // ---------------------------------------------------------------- epilogue (TMEM lanes 32w..32w+31)
+  } else if (warp < 8) {
+    // ---------------------------------------------------------------- epilogue
+    // Two groups of four warps (warp w reads TMEM lanes 32*(w%4)..+31) take alternate 16-column
+    // strips; inside a group the residual / accumulator loads of the NEXT strip are issued before
+    // the current strip is stored, so ~2 x 16 loads per thread are in flight (the epilogue is a
+    // DRAM-latency pipeline: measured 1.4 us per strip when each strip waited for its own loads).
+    const int grp = warp >> 2, wq = warp & 3;
+    const int nstrips = p.Cp / 16;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
+      const int b = tile / tpi, t0 = (tile - b * tpi) * TC_M;
+      const int t = t0 + wq * 32 + lane;
+      const bool live = t < p.L;
+      const long long rowb = (long long)b * p.C * p.L + t;
+      auto load_adds = [&](int strip, float (&add)[16]) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int co = strip * 16 + j;
+          float a = 0.f;
+          if (live && co < p.C) {
+            const long long off = rowb + (long long)co * p.L;
+            if (p.res) a = p.res[off];
+            if (p.accum) a += p.y[off];
+          }
+          add[j] = a;
+        }
+      };
+      float cur[16], nxt[16];
+      if (grp < nstrips) load_adds(grp, cur);   // independent of the accumulator: overlaps the MMA
       tc::mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
       tc::fence_after_sync();
-      const int b = tile / tpi, t0 = (tile - b * tpi) * TC_M;
-      const int t = t0 + warp * 32 + lane;
-      const long long rowb = (long long)b * p.C * p.L;
-      const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * acc_stride);
-      for (int c0 = 0; c0 < p.Cp; c0 += 16) {
+      const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_stride);
+      for (int strip = grp; strip < nstrips; strip += 2) {
         uint32_t v[16];
-        tc::tmem_ld16(tbase + (uint32_t)c0, v);
+        tc::tmem_ld16(tbase + (uint32_t)(strip * 16), v);
+        if (strip + 2 < nstrips) load_adds(strip + 2, nxt);
         tc::tmem_ld_wait();
-        if (t < p.L) {
+        if (live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const int co = c0 + j;
+            const int co = strip * 16 + j;
             if (co < p.C) {
-              const long long off = rowb + (long long)co * p.L + t;
-              float o = __uint_as_float(v[j]) + __ldg(p.bias + co);
-              if (p.res) o += p.res[off];
-              if (p.accum) o += p.y[off];
+              float o = __uint_as_float(v[j]) + __ldg(p.bias + co) + cur[j];
               if (p.out_div != 0.f) o = o / p.out_div;
-              p.y[off] = o;
+              p.y[rowb + (long long)co * p.L] = o;
             }
           }
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cur[j] = nxt[j];
       }
       tc::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&t_empty[acc])) : "memory");
@@ -331,7 +372,7 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, ncols);
+  if (warp == 8) tc::tmem_dealloc(tmem, ncols);
 }
 
 static AmpPlan amp_plan(int Cp, int K, int dil, int nsplit) {
@@ -376,14 +417,16 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
     SVCB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   }
   int occ = 1;
-  SVCB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, amp_conv_tc_kernel, 192, pl.smem));
+  SVCB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, amp_conv_tc_kernel, 320, pl.smem));
   occ = std::max(1, std::min(occ, 512 / pl.ncols));
   const int ntiles = p.B * ((p.L + TC_M - 1) / TC_M);
   const int grid = std::min(ntiles, n_sm * occ);
   const double macs = (double)p.B * p.L * p.C * p.C * p.K;
-  KernelScope ks(p.nsplit == 3 ? "amp_conv_tc_bf16x3" : "amp_conv_tc_bf16", s, 2.0 * macs,
+  char kname[64];
+  snprintf(kname, sizeof(kname), "amp_conv_tc_%s_c%dk%d", p.nsplit == 3 ? "bf16x3" : "bf16", p.C, p.K);
+  KernelScope ks(kname, s, 2.0 * macs,
                  (double)p.B * p.C * p.L * ((p.nsplit == 3 ? 4.0 : 2.0) + 4.0 * (p.res ? 2 : 1)));
-  amp_conv_tc_kernel<<<grid, 192, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols);
+  amp_conv_tc_kernel<<<grid, 320, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols);
   SVCB_LAUNCH_CHECK("amp_conv_tc");
   return SVCB_OK;
 }

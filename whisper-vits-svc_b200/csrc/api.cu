@@ -286,6 +286,21 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
   const int prec = m->cfg.precision;
   for (int j = 0; j < nres; ++j) {
     const ResBlock& R = m->res[stage * nres + j];
+    if (prec != 0 && amp_block_fused_supported(ch, R.k, R.dil)) {
+      // narrow stages: the whole block (6 convs + 6 SnakeAlias + residuals) in one fp32 kernel
+      AmpBlockParams q;
+      q.x = X; q.y = ACC; q.B = B; q.C = ch; q.L = L; q.K = R.k;
+      for (int d = 0; d < 3; ++d) {
+        q.dil[d] = R.dil[d];
+        q.w1[d] = R.c1[d].w; q.b1[d] = R.c1[d].b; q.w2[d] = R.c2[d].w; q.b2[d] = R.c2[d].b;
+      }
+      q.cout_pad = R.c1[0].cout_pad;
+      for (int a = 0; a < 6; ++a) { q.ea[a] = R.act[a].ea; q.ib[a] = R.act[a].ib; q.fu[a] = R.act[a].fu; q.fd[a] = R.act[a].fd; }
+      q.accum = j > 0;
+      if (j == nres - 1) q.out_div = (float)nres;
+      RUN(launch_amp_block_fused(q, s));
+      continue;
+    }
     const float* cur = X;
     for (int d = 0; d < 3; ++d) {
       const SnakeW& a1 = R.act[2 * d];

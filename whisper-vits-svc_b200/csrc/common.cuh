@@ -98,6 +98,21 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 size_t p8_image_bytes(int B, int C, int L);
 int p8_rows(int L);
 
+// ----------------------------------------------------------------------------- fused AMP block (C = 10, 20)
+struct AmpBlockParams {
+  const float* x = nullptr;      // [B, C, L] stage input
+  float* y = nullptr;            // [B, C, L] stage accumulator
+  int B = 0, C = 0, L = 0, K = 3;
+  int dil[3] = {1, 3, 5};
+  const float *w1[3], *b1[3], *w2[3], *b2[3];   // packed [ci][j][cout_pad] weights, [C] biases
+  int cout_pad = 0;
+  const float *ea[6], *ib[6], *fu[6], *fd[6];   // SnakeAlias parameters of activations 0..5
+  int accum = 0;                 // y = y_old + block(x)
+  float out_div = 0.f;           // then / out_div when != 0
+};
+int launch_amp_block_fused(const AmpBlockParams& p, cudaStream_t s);
+bool amp_block_fused_supported(int C, int K, const int* dil);
+
 // ----------------------------------------------------------------------------- general tensor-core conv
 struct ConvTcParams {
   const float* x = nullptr;

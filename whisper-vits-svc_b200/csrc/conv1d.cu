@@ -12,6 +12,7 @@
 // x tile [CI_T][span] and weight tile [CI_T][K][8*COG] (co innermost -> two LDS.128 per tap).
 #include <algorithm>
 #include <climits>
+#include <cstdio>
 
 #include "common.cuh"
 
@@ -179,7 +180,9 @@ static int launch_t(const ConvParams& p, int cog, int ci_tile, int xspan, size_t
   dim3 block(32, cog);
   dim3 grid((p.nq + 32 * TPT - 1) / (32 * TPT), (p.cout_pad / 8 + cog - 1) / cog, p.B);
   const int cout_real = (p.flags & CONV_GATE) ? p.Cout / 2 : p.Cout;
-  KernelScope ks("conv1d_fp32", s, 2.0 * p.Cin * p.K * p.Cout * (double)p.nq * p.B,
+  char kname[64];
+  snprintf(kname, sizeof(kname), "conv1d_fp32_%dto%d_k%d_o%d", p.Cin, p.Cout, p.K, p.out_mul);
+  KernelScope ks(kname, s, 2.0 * p.Cin * p.K * p.Cout * (double)p.nq * p.B,
                  4.0 * ((double)p.B * p.Cin * p.nq * p.stride + (double)p.B * cout_real * p.nq * (p.res ? 2 : 1) +
                         (double)p.Cin * p.K * p.Cout));
   conv1d_kernel<TPT><<<grid, block, smem, s>>>(p, ci_tile, xspan);

@@ -125,15 +125,23 @@ conv_tc_kernel(const ConvTcParams p) {
     for (int c0 = 0; c0 < p.bn; c0 += 16) {
       uint32_t v[16];
       tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      const bool live = t < p.Tout;
+      const int step = gate ? 2 : 1;
+      // residual / accumulator loads of the strip first (all in flight), stores afterwards
+      float add[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float a = 0.f;
+        const int cp = nt * p.bn + c0 + j;
+        if (live && (j % step) == 0 && cp + (step - 1) < p.Cout) {
+          const long long off = (long long)(gate ? (cp >> 1) : cp) * p.Tout + t;
+          if (rb) a = rb[off];
+          if (p.flags & CONV_ACCUM) a += yb[off];
+        }
+        add[j] = a;
+      }
       tc::tmem_ld_wait();
-      if (t < p.Tout) {
-        auto finish = [&](float o, int co) {
-          if (!keep) o = 0.f;
-          const long long off = (long long)co * p.Tout + t;
-          if (rb) o += rb[off];
-          if (p.flags & CONV_ACCUM) o += yb[off];
-          yb[off] = o;
-        };
+      if (live) {
         if (gate) {
 #pragma unroll
           for (int j = 0; j < 16; j += 2) {
@@ -141,7 +149,9 @@ conv_tc_kernel(const ConvTcParams p) {
             if (cp + 1 < p.Cout) {
               const float a = __uint_as_float(v[j]) + __ldg(p.bias + cp);
               const float g = __uint_as_float(v[j + 1]) + __ldg(p.bias + cp + 1);
-              finish(tanhf(a) * (1.f / (1.f + expf(-g))), cp >> 1);
+              float o = tanhf(a) * (1.f / (1.f + expf(-g)));
+              if (!keep) o = 0.f;
+              yb[(long long)(cp >> 1) * p.Tout + t] = o + add[j];
             }
           }
         } else {
@@ -149,8 +159,9 @@ conv_tc_kernel(const ConvTcParams p) {
           for (int j = 0; j < 16; ++j) {
             const int co = nt * p.bn + c0 + j;
             if (co < p.Cout) {
-              float o = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + co) : 0.f);
-              finish(ct_act(o, p.act), co);
+              float o = ct_act(__uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + co) : 0.f), p.act);
+              if (!keep) o = 0.f;
+              yb[(long long)co * p.Tout + t] = o + add[j];
             }
           }
         }

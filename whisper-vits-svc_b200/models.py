@@ -7,6 +7,10 @@ libsvc_b200.so through the C ABI (include/svcb.h).  PyTorch is only the owner of
 and streams here.  There is no CPU path: calling a compute method without a CUDA device, or
 without the built library, raises.
 
+`precision` selects how the dense convolutions are computed: 3 (default) =
+bf16x3-split tcgen05 MMAs + fused fp32 narrow stages (meets the 1e-3 waveform gate, ~1e-5 measured),
+1 = plain bf16 MMAs (faster, ~4e-3), 0 = all-fp32 CUDA-core kernels (device-side reference).
+
 The reference draws three random tensors internally (vits/models.py:51,
 vits_decoder/nsf.py:232-236,311); they are explicit keyword arguments here (`eps`, `rand_ini`,
 `noise`) defaulting to fresh torch draws on the model's device, which is how parity tests inject
@@ -24,7 +28,7 @@ from . import _lib, pack, synth
 
 
 class SynthesizerInfer(torch.nn.Module):
-    def __init__(self, spec_channels, segment_size, hp, precision: int = 0):
+    def __init__(self, spec_channels, segment_size, hp, precision: int = 3):
         super().__init__()
         self.segment_size = segment_size  # unused at inference, kept for signature parity
         self.hp = hp
