@@ -203,3 +203,35 @@ def test_full_size_tensor_core_mode(model_tc, hp, sd):
     err = max_abs(wave[:1], wave_o)
     print(f"10 s item (precision 3): wave max-abs err {err:.3e}")
     assert torch.isfinite(wave).all() and err <= 2e-4
+
+
+def test_svc_infer_chunk_loop_vs_oracle(model_tc, hp, sd, tmp_path):
+    """SURVEY.md §8a row a17 / config #1 plumbing: the host loop of svc_inference.py:77-134 (2500-frame
+    chunks, +-10-frame overlap discarded, last sample dropped) through hostio.svc_infer, against the
+    same loop restated over the oracle chunk by chunk, with the reference's random draws injected."""
+    from whisper_vits_svc_b200 import hostio
+    n = 2600  # -> chunks (0,2510) and (2490,2600)
+    g = torch.Generator().manual_seed(17)
+    ppg = torch.randn(n, hp.vits.ppg_dim, generator=g)
+    vec = torch.randn(n + 3, hp.vits.vec_dim, generator=g)  # ragged feature lengths are trimmed to the min
+    pit = torch.randint(100, 500, (n + 1,), generator=g).float()
+    pit[700:900] = 0
+    spk = torch.randn(hp.vits.spk_dim, generator=g) * 0.05
+    rand_ini = torch.rand(1, 11, generator=g)
+    noise = torch.randn(1, n * 320, 11, generator=g)
+    plan = hostio.chunk_plan(n, 320)
+    assert [(c[0], c[1]) for c in plan] == [(0, 2510), (2490, 2600)]
+    eps = {i: torch.randn(1, hp.vits.inter_channels, ce - cs, generator=g) for i, (cs, ce, _, _) in enumerate(plan)}
+    out = hostio.svc_infer(model_tc, spk, pit, ppg, vec, hp, "cuda", write_pit_wav=None, rand_ini=rand_ini,
+                           noise=noise, eps_fn=lambda i, b, t: eps[i])
+    assert out.dtype == np.float32 and out.shape == (n * 320 - 1,)
+    src = O.pitch2source(sd, hp, pit[:n][None], rand_ini, noise)
+    ref = []
+    for i, (cs, ce, so, eo) in enumerate(plan):
+        w = O.synthesizer_infer(sd, hp, ppg[None, cs:ce], vec[None, cs:ce], pit[None, cs:ce], spk[None],
+                                torch.tensor([ce - cs]), src[:, :, cs * 320:ce * 320], eps[i])
+        ref.append(w[0, 0].numpy()[so:eo])
+    ref = np.concatenate(ref)
+    err = float(np.abs(out - ref).max())
+    print(f"svc_infer 26 s utterance, 2 chunks: max-abs {err:.3e}")
+    assert err <= 2e-4

@@ -36,6 +36,7 @@ template <int C>
 struct AbCfg {
   static constexpr int CP = (C + 3) / 4 * 4;
   static constexpr int TOUT = C <= 10 ? 1024 : 512;
+  static constexpr int NT = 2;   // time steps per thread in the convolution
 };
 
 // SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
@@ -43,7 +44,7 @@ struct AbCfg {
 // 2x-rate Snake values of its chunk in its own scratch slice and decimates them — only __syncwarp,
 // no CTA barrier inside the activation.
 constexpr int AB_CH = 64;
-constexpr int AB_VSL = 2 * (AB_CH + 6) + 4;  // scratch floats per warp
+constexpr int AB_VSL = 2 * (AB_CH + 6) + 4;  // scratch floats per warp (slot 0 unused: tap 0 lands on an even index)
 
 template <int C>
 __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst, float* V,
@@ -78,11 +79,11 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
       uo = fmaf(x[5], fu[2], uo); uo = fmaf(x[6], fu[0], uo);
       ue *= 2.f; uo *= 2.f;
       const float se = __sinf(ue * a_), so = __sinf(uo * a_);
-      vw[2 * ai] = fmaf(b_, se * se, ue);        // v[2a]   at j = m - 2*(n0-3)
-      vw[2 * ai + 1] = fmaf(b_, so * so, uo);    // v[2a+1]
+      vw[2 * ai + 1] = fmaf(b_, se * se, ue);    // v[2a]   at j = m - 2*(n0-3) + 1
+      vw[2 * ai + 2] = fmaf(b_, so * so, uo);    // v[2a+1]
     }
     __syncwarp();
-    const int jbase = 2 * (n0 - 3);
+    const int jbase = 2 * (n0 - 3) - 1;
     for (int ni = lane; ni < AB_CH; ni += 32) {
       const int n = n0 + ni;
       if (n >= W) break;
@@ -90,9 +91,13 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
       if (n >= lo_i && n <= hi_i) {
         const int m0 = 2 * n - 5;
         if (m0 >= mlo && m0 + 11 <= mhi) {
-          const float* vp = vw + (m0 - jbase);
+          const float2* vp = reinterpret_cast<const float2*>(vw + (m0 - jbase));  // even index
 #pragma unroll
-          for (int k = 0; k < 12; ++k) o = fmaf(vp[k], fdn[k], o);
+          for (int k = 0; k < 6; ++k) {
+            const float2 v2 = vp[k];
+            o = fmaf(v2.x, fdn[2 * k], o);
+            o = fmaf(v2.y, fdn[2 * k + 1], o);
+          }
         } else {
 #pragma unroll
           for (int k = 0; k < 12; ++k) o = fmaf(vw[min(max(m0 + k, mlo), mhi) - jbase], fdn[k], o);
@@ -105,50 +110,57 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
 }
 
 // dst[co][t] = bias[co] + sum_ci sum_j w[ci][j][co] * src[ci][t + j*dil - P]  (+ dst[co][t] if RES);
-// a thread owns two time steps (t, t + AB_THREADS) so every weight vector load feeds 2*C FMAs.
+// a thread owns NT time steps (t + i*AB_THREADS) so every weight vector load feeds NT*C FMAs.
 template <int C, bool RES>
 __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __restrict__ dst,
                                         const float* __restrict__ wsm, const float* __restrict__ bsm,
                                         int K, int dil, int W, int WS, int lo_i, int hi_i, int tid) {
   constexpr int CP = AbCfg<C>::CP;
+  constexpr int NT = AbCfg<C>::NT;
   const int P = dil * (K - 1) / 2;
-  for (int tb = tid; tb < W; tb += 2 * AB_THREADS) {
-    const int t1 = tb + AB_THREADS;
-    const bool two = t1 < W;
-    float acc0[CP], acc1[CP];
+  for (int tb = tid; tb < W; tb += NT * AB_THREADS) {
+    float acc[NT][CP];
+    int toff[NT];
 #pragma unroll
-    for (int co = 0; co < CP; ++co) { acc0[co] = co < C ? bsm[co] : 0.f; acc1[co] = acc0[co]; }
-    const float* sp0 = src + AB_GUARD + tb - P;
-    const float* sp1 = src + AB_GUARD + (two ? t1 : tb) - P;
+    for (int i = 0; i < NT; ++i) {
+      const int t = tb + i * AB_THREADS;
+      toff[i] = (t < W ? t : tb) - P + AB_GUARD;
+#pragma unroll
+      for (int co = 0; co < CP; ++co) acc[i][co] = co < C ? bsm[co] : 0.f;
+    }
     for (int ci = 0; ci < C; ++ci) {
-      const float* s0 = sp0 + ci * WS;
-      const float* s1 = sp1 + ci * WS;
+      const float* sr = src + ci * WS;
       const float* wr = wsm + ci * K * CP;
       for (int j = 0; j < K; ++j) {
-        const float x0 = s0[j * dil], x1 = s1[j * dil];
+        float xv[NT];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) xv[i] = sr[toff[i] + j * dil];
         const float4* w4 = reinterpret_cast<const float4*>(wr + j * CP);
 #pragma unroll
         for (int q = 0; q < CP / 4; ++q) {
           const float4 w = w4[q];
-          acc0[4 * q + 0] = fmaf(x0, w.x, acc0[4 * q + 0]); acc1[4 * q + 0] = fmaf(x1, w.x, acc1[4 * q + 0]);
-          acc0[4 * q + 1] = fmaf(x0, w.y, acc0[4 * q + 1]); acc1[4 * q + 1] = fmaf(x1, w.y, acc1[4 * q + 1]);
-          acc0[4 * q + 2] = fmaf(x0, w.z, acc0[4 * q + 2]); acc1[4 * q + 2] = fmaf(x1, w.z, acc1[4 * q + 2]);
-          acc0[4 * q + 3] = fmaf(x0, w.w, acc0[4 * q + 3]); acc1[4 * q + 3] = fmaf(x1, w.w, acc1[4 * q + 3]);
+#pragma unroll
+          for (int i = 0; i < NT; ++i) {
+            acc[i][4 * q + 0] = fmaf(xv[i], w.x, acc[i][4 * q + 0]);
+            acc[i][4 * q + 1] = fmaf(xv[i], w.y, acc[i][4 * q + 1]);
+            acc[i][4 * q + 2] = fmaf(xv[i], w.z, acc[i][4 * q + 2]);
+            acc[i][4 * q + 3] = fmaf(xv[i], w.w, acc[i][4 * q + 3]);
+          }
         }
       }
     }
-    const bool in0 = tb >= lo_i && tb <= hi_i, in1 = two && t1 >= lo_i && t1 <= hi_i;
 #pragma unroll
-    for (int co = 0; co < C; ++co) {
-      float* d0 = dst + co * WS + AB_GUARD + tb;
-      float o0 = acc0[co];
-      if (RES) o0 += *d0;
-      *d0 = in0 ? o0 : 0.f;
-      if (two) {
-        float* d1 = dst + co * WS + AB_GUARD + t1;
-        float o1 = acc1[co];
-        if (RES) o1 += *d1;
-        *d1 = in1 ? o1 : 0.f;
+    for (int i = 0; i < NT; ++i) {
+      const int t = tb + i * AB_THREADS;
+      if (t < W) {
+        const bool inside = t >= lo_i && t <= hi_i;
+#pragma unroll
+        for (int co = 0; co < C; ++co) {
+          float* d = dst + co * WS + AB_GUARD + t;
+          float o = acc[i][co];
+          if (RES) o += *d;
+          *d = inside ? o : 0.f;
+        }
       }
     }
   }

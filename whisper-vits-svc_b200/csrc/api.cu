@@ -182,6 +182,54 @@ static int launch_mask_mul(float* x, const long long* lengths, int B, int C, int
   return SVCB_OK;
 }
 
+// ----------------------------------------------------------------------------- upsampler finalize
+// The ConvTranspose1d upsamplers (generator.py:183) run as `rate` polyphase sub-convolutions.  Each
+// phase writes its outputs CONTIGUOUSLY into a phase-major scratch (coalesced stores); this kernel
+// interleaves the phases back into y[b, co, n], adds the transposed conv's bias and, for the stages
+// whose noise conv is short (K <= 8), noise_convs[i](source) + its bias (generator.py:185-186) in
+// the same pass — one coalesced write of the stage input instead of `rate` strided ones plus a
+// read-modify-write.
+struct UpsFinalizeParams {
+  const float* tmp[SVCB_MAX_UPS];  // per phase r: [B][C][nq[r]]
+  int nq[SVCB_MAX_UPS], q0[SVCB_MAX_UPS];
+  const float* bias;               // [C]
+  const float* src;                // [B][Ltot] or null (noise handled elsewhere)
+  const float* wn;                 // packed [1][Kn][cout_pad]
+  const float* bn;                 // [C]
+  float* y;                        // [B][C][Ln]
+  int C, Ln, rate, pad, Kn, sf, padn, cout_pad;
+  long long Ltot;
+};
+
+__global__ void __launch_bounds__(256)
+ups_finalize_kernel(const UpsFinalizeParams p) {
+  const int n = blockIdx.x * 256 + threadIdx.x, co = blockIdx.y, b = blockIdx.z;
+  if (n >= p.Ln) return;
+  const int r = (n + p.pad) % p.rate, q = (n + p.pad) / p.rate;
+  const int qi = q - p.q0[r];
+  float v = __ldg(p.bias + co);
+  if (qi >= 0 && qi < p.nq[r]) v += p.tmp[r][((long long)b * p.C + co) * p.nq[r] + qi];
+  if (p.src) {
+    const float* sb = p.src + (long long)b * p.Ltot;
+    float a = __ldg(p.bn + co);
+    for (int j = 0; j < p.Kn; ++j) {
+      const long long si = (long long)n * p.sf + j - p.padn;
+      if (si >= 0 && si < p.Ltot) a = fmaf(__ldg(sb + si), __ldg(p.wn + (long long)j * p.cout_pad + co), a);
+    }
+    v += a;
+  }
+  p.y[((long long)b * p.C + co) * p.Ln + n] = v;
+}
+
+static int launch_ups_finalize(const UpsFinalizeParams& p, int B, cudaStream_t s) {
+  dim3 grid((p.Ln + 255) / 256, p.C, B);
+  KernelScope ks("ups_finalize", s, 2.0 * B * p.C * (double)p.Ln * (p.src ? p.Kn : 0),
+                 8.0 * B * p.C * (double)p.Ln);
+  ups_finalize_kernel<<<grid, 256, 0, s>>>(p);
+  SVCB_LAUNCH_CHECK("ups_finalize");
+  return SVCB_OK;
+}
+
 // ----------------------------------------------------------------------------- prior encoder
 static int run_prior(const svcb_model* m, Ctx& ctx, const float* ppg, const float* vec,
                      const float* pit, const long long* lengths, const float* eps, float* z_p, int B,
@@ -393,21 +441,34 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     float* X = ctx.alloc<float>((size_t)B * chn * Ln);
     float* ACC = ctx.alloc<float>((size_t)B * chn * Ln);
     SVCB_TRY(check_ws(ctx));
-    // ConvTranspose1d as `rate` polyphase sub-convolutions (generator.py:183)
+    // ConvTranspose1d as `rate` polyphase sub-convolutions (generator.py:183), each into its own
+    // contiguous slab of T1 (coalesced), interleaved + biased + (short) noise conv by ups_finalize
+    int sf = 1;
+    for (int k2 = i + 1; k2 < c.n_ups; ++k2) sf *= c.up_rates[k2];
+    const bool last = (i + 1 == c.n_ups);
+    const int Kn = us.noise.k;
+    const bool fuse_noise = Kn <= 8;
+    UpsFinalizeParams fp;
+    fp.bias = us.bias; fp.y = X; fp.C = chn; fp.Ln = Ln; fp.rate = us.rate; fp.pad = us.pad;
+    fp.src = fuse_noise ? source : nullptr; fp.wn = us.noise.w; fp.bn = us.noise.b; fp.Kn = Kn;
+    fp.sf = last ? 1 : sf; fp.padn = last ? 0 : sf / 2; fp.cout_pad = us.noise.cout_pad; fp.Ltot = Ltot;
+    size_t slab = 0;
     for (int r = 0; r < us.rate; ++r) {
-      ConvParams p = std_conv(us.phase[r], x, X, B, L, Ln, us.taps - 1);
-      p.bias = us.bias;
+      ConvParams p = std_conv(us.phase[r], x, nullptr, B, L, Ln, us.taps - 1);
+      p.bias = nullptr;
       const int pr = us.pad - r;
       p.q0 = pr > 0 ? (pr + us.rate - 1) / us.rate : 0;
       const int qmax = (Ln - 1 + us.pad - r) / us.rate;
       p.nq = qmax - p.q0 + 1;
-      p.out_mul = us.rate; p.out_off = r - us.pad;
+      p.y = T1 + slab;
+      p.syb = (long long)chn * p.nq; p.syc = p.nq; p.syt = 1;
+      p.out_mul = 1; p.out_off = -p.q0;
+      fp.tmp[r] = p.y; fp.nq[r] = p.nq; fp.q0[r] = p.q0;
+      slab += (size_t)B * chn * p.nq;
       RUN(launch_conv1d(p, s));
     }
-    {  // noise_convs[i](har_source) added in place (generator.py:185-186)
-      int sf = 1;
-      for (int k2 = i + 1; k2 < c.n_ups; ++k2) sf *= c.up_rates[k2];
-      const bool last = (i + 1 == c.n_ups);
+    if (!ctx.dry) SVCB_TRY(launch_ups_finalize(fp, B, s));
+    if (!fuse_noise) {  // long noise filters (K = 2*prod(later rates)): separate accumulate pass
       ConvParams p;
       p.x = source; p.sxb = Ltot; p.sxc = Ltot; p.sxt = 1;
       p.w = us.noise.w; p.cout_pad = us.noise.cout_pad; p.bias = us.noise.b;

@@ -183,6 +183,8 @@ conv_tc_kernel(const ConvTcParams p) {
     const uint32_t idesc = tc::idesc_bf16(CT_M, p.bn);
     const uint32_t a_base = tc::smem_u32(A0), w_base = tc::smem_u32(W0);
     const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.bn * 16u;
+    const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;
+    const int nk = p.kch / 16;
     uint32_t accumulate = 0;
     int wi = 0;
     for (int cc = 0; cc < ncc; ++cc) {
@@ -196,15 +198,16 @@ conv_tc_kernel(const ConvTcParams p) {
           const int st = wi % CT_WST;
           tc::mbar_wait(&w_full[st], (uint32_t)((wi / CT_WST) & 1));
           tc::fence_after_sync();
-          const uint32_t wb = w_base + (uint32_t)st * w_tile;
+          const uint64_t bd0 = tc::smem_desc(w_base + (uint32_t)st * w_tile, lbo_b);
           const int n_a = (part == 0 && nparts == 2) ? 2 : 1;
           for (int ap = 0; ap < n_a; ++ap) {
-            const uint32_t ab = (ap == 0 ? ah : al) + row_off;
-            for (int kk = 0; kk < p.kch / 16; ++kk) {
-              const uint64_t ad = tc::smem_desc(ab + (uint32_t)kk * 2u * lbo_a, lbo_a);
-              const uint64_t bd = tc::smem_desc(wb + (uint32_t)kk * 2u * lbo_b, lbo_b);
+            uint64_t ad = tc::smem_desc((ap == 0 ? ah : al) + row_off, lbo_a);
+            uint64_t bd = bd0;
+            for (int kk = 0; kk < nk; ++kk) {
               tc::mma_bf16(tmem, ad, bd, idesc, accumulate);
               accumulate = 1;
+              ad += kstep_a;
+              bd += kstep_b;
             }
           }
           tc::mma_commit(&w_empty[st]);
