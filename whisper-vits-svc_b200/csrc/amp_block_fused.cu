@@ -23,7 +23,6 @@
 
 namespace svcb {
 
-constexpr int AB_THREADS = 512;
 constexpr int AB_GUARD = 32;   // zeroed floats on both sides of every row (>= max conv reach 25)
 
 __host__ __device__ inline int ab_halo(int K, const int* dil) {
@@ -36,7 +35,8 @@ template <int C>
 struct AbCfg {
   static constexpr int CP = (C + 3) / 4 * 4;
   static constexpr int TOUT = C <= 10 ? 1024 : 512;
-  static constexpr int NT = 2;   // time steps per thread in the convolution
+  static constexpr int THREADS = C <= 10 ? 1024 : 512;   // 32 warps when the register budget allows
+  static constexpr int NT = 2;                           // time steps per thread in the convolution
 };
 
 // SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
@@ -50,6 +50,7 @@ template <int C>
 __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst, float* V,
                                          const float* f_up, const float* f_dn, const float* ea,
                                          const float* ib, int W, int WS, int lo_i, int hi_i, int tid) {
+  constexpr int AB_THREADS = AbCfg<C>::THREADS;
   const int warp = tid >> 5, lane = tid & 31;
   float* vw = V + warp * AB_VSL;
   const int nchunks = (W + AB_CH - 1) / AB_CH;
@@ -111,12 +112,13 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
 
 // dst[co][t] = bias[co] + sum_ci sum_j w[ci][j][co] * src[ci][t + j*dil - P]  (+ dst[co][t] if RES);
 // a thread owns NT time steps (t + i*AB_THREADS) so every weight vector load feeds NT*C FMAs.
-template <int C, bool RES>
+template <int C, int K, bool RES>
 __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __restrict__ dst,
                                         const float* __restrict__ wsm, const float* __restrict__ bsm,
-                                        int K, int dil, int W, int WS, int lo_i, int hi_i, int tid) {
+                                        int dil, int W, int WS, int lo_i, int hi_i, int tid) {
   constexpr int CP = AbCfg<C>::CP;
   constexpr int NT = AbCfg<C>::NT;
+  constexpr int AB_THREADS = AbCfg<C>::THREADS;
   const int P = dil * (K - 1) / 2;
   for (int tb = tid; tb < W; tb += NT * AB_THREADS) {
     float acc[NT][CP];
@@ -131,6 +133,7 @@ __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __
     for (int ci = 0; ci < C; ++ci) {
       const float* sr = src + ci * WS;
       const float* wr = wsm + ci * K * CP;
+#pragma unroll
       for (int j = 0; j < K; ++j) {
         float xv[NT];
 #pragma unroll
@@ -166,9 +169,10 @@ __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __
   }
 }
 
-template <int C>
-__global__ void __launch_bounds__(AB_THREADS, 1)
+template <int C, int K>
+__global__ void __launch_bounds__(AbCfg<C>::THREADS, 1)
 amp_block_fused_kernel(const AmpBlockParams p) {
+  constexpr int AB_THREADS = AbCfg<C>::THREADS;
   constexpr int CP = AbCfg<C>::CP;
   constexpr int TOUT = AbCfg<C>::TOUT;
   extern __shared__ __align__(16) float ab_smem[];
@@ -176,7 +180,6 @@ amp_block_fused_kernel(const AmpBlockParams p) {
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * TOUT;
-  const int K = p.K;
   const int H = ab_halo(K, p.dil);
   const int W = TOUT + 2 * H;
   const int WS = W + 2 * AB_GUARD;
@@ -216,11 +219,11 @@ amp_block_fused_kernel(const AmpBlockParams p) {
       if (half == 0) {
         ab_snake<C>(X, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
         __syncthreads();
-        ab_conv<C, false>(Y, Z, wsm, s_bias, K, p.dil[d], W, WS, lo_i, hi_i, tid);
+        ab_conv<C, K, false>(Y, Z, wsm, s_bias, p.dil[d], W, WS, lo_i, hi_i, tid);
       } else {
         ab_snake<C>(Z, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
         __syncthreads();
-        ab_conv<C, true>(Y, X, wsm, s_bias, K, 1, W, WS, lo_i, hi_i, tid);
+        ab_conv<C, K, true>(Y, X, wsm, s_bias, 1, W, WS, lo_i, hi_i, tid);
       }
       __syncthreads();
     }
@@ -240,15 +243,16 @@ amp_block_fused_kernel(const AmpBlockParams p) {
   }
 }
 
-template <int C>
+template <int C, int K>
 static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
+  constexpr int AB_THREADS = AbCfg<C>::THREADS;
   const int H = ab_halo(p.K, p.dil);
   const int W = AbCfg<C>::TOUT + 2 * H, WS = W + 2 * AB_GUARD;
   const size_t smem = ((size_t)3 * C * WS + (AB_THREADS / 32) * AB_VSL + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
   if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   dim3 grid((p.L + AbCfg<C>::TOUT - 1) / AbCfg<C>::TOUT, p.B);
@@ -256,13 +260,14 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);
   KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B + 6 * 70.0 * C * (double)p.L * p.B,
                  (p.accum ? 12.0 : 8.0) * C * (double)p.L * p.B);
-  amp_block_fused_kernel<C><<<grid, AB_THREADS, smem, s>>>(p);
+  amp_block_fused_kernel<C, K><<<grid, AB_THREADS, smem, s>>>(p);
   SVCB_LAUNCH_CHECK("amp_block_fused");
   return SVCB_OK;
 }
 
 bool amp_block_fused_supported(int C, int K, const int* dil) {
   if (C != 10 && C != 20) return false;
+  if (K != 3 && K != 7 && K != 11) return false;
   for (int d = 0; d < 3; ++d) if (dil[d] * (K - 1) / 2 > AB_GUARD) return false;
   return true;
 }
@@ -270,7 +275,8 @@ bool amp_block_fused_supported(int C, int K, const int* dil) {
 int launch_amp_block_fused(const AmpBlockParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.L <= 0) return SVCB_OK;
   if (!amp_block_fused_supported(p.C, p.K, p.dil)) { set_error("amp_block_fused: unsupported channel count / reach"); return SVCB_E_UNSUPPORTED; }
-  return p.C == 10 ? launch_ab<10>(p, s) : launch_ab<20>(p, s);
+  if (p.C == 10) return p.K == 3 ? launch_ab<10, 3>(p, s) : p.K == 7 ? launch_ab<10, 7>(p, s) : launch_ab<10, 11>(p, s);
+  return p.K == 3 ? launch_ab<20, 3>(p, s) : p.K == 7 ? launch_ab<20, 7>(p, s) : launch_ab<20, 11>(p, s);
 }
 
 }  // namespace svcb
