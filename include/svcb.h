@@ -165,10 +165,14 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
                         void* ws, size_t ws_bytes, svcb_stream stream);
 
 /* Operator entry points of the encoder (unit tests):
- * out[M,N] = A[M,K] . W[N,K]^T + bias with epilogue 0: bf16 out, 1: GELU(erf) then bf16 out,
- * 2: + res (fp32 [M,N]) -> fp32 out.  A, W bf16 row-major; N % 128 == 0, K % 64 == 0. */
+ * out[M,N] = A[M,K] . W[N,K]^T + bias with epilogue 0: bf16 row-major out, 1: GELU(erf) then bf16
+ * out as the GEMM tile image ([ceil(M/128)][N/64][8][128][8], the A operand of a following GEMM),
+ * 2: + res (fp32 [M,N]) -> fp32 out.  A, W bf16 row-major (converted to tile images in `scratch`);
+ * N % 256 == 0, K % 64 == 0. */
+size_t svcb_op_gemm_bf16_scratch_bytes(int32_t M, int32_t N, int32_t K);
 int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
-                      int32_t M, int32_t N, int32_t K, int32_t epilogue, svcb_stream stream);
+                      int32_t M, int32_t N, int32_t K, int32_t epilogue, void* scratch, size_t scratch_bytes,
+                      svcb_stream stream);
 /* softmax(q k^T / sqrt(64)) v per head: qkv bf16 [B*T, 3*D] rows (q|k|v), out bf16 [B*T, D]. */
 int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
                            svcb_stream stream);

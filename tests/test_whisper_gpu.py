@@ -19,8 +19,15 @@ def _s():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-@pytest.mark.parametrize("M,N,K,epi", [(128, 128, 64, 0), (300, 256, 128, 0), (1000, 384, 1280, 1), (257, 1280, 320, 2),
-                                       (3000, 3840, 1280, 0)])
+def _from_image(img, M, N):
+    """GEMM tile image [ceil(M/128)][N/64][8][128][8] -> row-major [M, N]"""
+    mt = (M + 127) // 128
+    t = img.view(mt, N // 64, 8, 128, 8).permute(0, 3, 1, 2, 4).reshape(mt * 128, N)
+    return t[:M]
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 256, 64, 0), (300, 256, 128, 0), (1000, 512, 1280, 1), (257, 1280, 320, 2),
+                                       (3000, 3840, 1280, 0), (24000, 1280, 1280, 2)])
 def test_gemm_bf16(M, N, K, epi):
     from whisper_vits_svc_b200 import _lib
     g = torch.Generator().manual_seed(M + N + K)
@@ -28,19 +35,27 @@ def test_gemm_bf16(M, N, K, epi):
     Wt = (torch.randn(N, K, generator=g) / K ** 0.5).bfloat16()
     bias = torch.randn(N, generator=g)
     res = torch.randn(M, N, generator=g)
-    ref = A.float() @ Wt.float().t() + bias
+    Ad, Wd, bd, rd = A.cuda(), Wt.cuda(), bias.cuda(), res.cuda()
+    ref = Ad.float() @ Wd.float().t() + bd          # fp32 reference on the device (same bf16 inputs)
     if epi == 1:
         ref = F.gelu(ref)
     if epi == 2:
-        ref = ref + res
-    Ad, Wd, bd, rd = A.cuda(), Wt.cuda(), bias.cuda(), res.cuda()
-    out = torch.zeros(M, N, device="cuda", dtype=torch.float32 if epi == 2 else torch.bfloat16)
-    st = _lib.load().svcb_op_gemm_bf16(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
-                                       rd.data_ptr() if epi == 2 else None, M, N, K, epi, _s())
+        ref = ref + rd
+    Mp = (M + 127) // 128 * 128
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.svcb_op_gemm_bf16_scratch_bytes(M, N, K)), dtype=torch.uint8, device="cuda")
+    if epi == 2:
+        out = torch.zeros(M, N, device="cuda", dtype=torch.float32)
+    else:
+        out = torch.zeros(Mp if epi == 1 else M, N, device="cuda", dtype=torch.bfloat16)
+    st = lib.svcb_op_gemm_bf16(Ad.data_ptr(), Wd.data_ptr(), bd.data_ptr(), out.data_ptr(),
+                               rd.data_ptr() if epi == 2 else None, M, N, K, epi, scratch.data_ptr(),
+                               scratch.numel(), _s())
     _lib.check(st, "svcb_op_gemm_bf16")
     torch.cuda.synchronize()
+    got = _from_image(out, M, N) if epi == 1 else out
     tol = 2e-4 * K ** 0.5 if epi == 2 else 3e-2   # bf16 output rounding dominates for epi 0/1
-    assert max_abs(out.float(), ref) <= tol
+    assert max_abs(got.float(), ref) <= tol
 
 
 @pytest.mark.parametrize("B,T,heads", [(2, 100, 2), (1, 64, 4), (2, 1500, 2), (1, 333, 20)])
@@ -59,7 +74,7 @@ def test_attention_bf16(B, T, heads):
     assert max_abs(out.float(), ref) <= 2e-2
 
 
-@pytest.mark.parametrize("state,heads,layers,B,n", [(128, 2, 4, 2, 200), (256, 4, 4, 1, 301), (1280, 20, 4, 1, 400)])
+@pytest.mark.parametrize("state,heads,layers,B,n", [(256, 4, 4, 2, 200), (512, 8, 4, 1, 301), (1280, 20, 4, 1, 400)])
 def test_encoder_vs_oracle(state, heads, layers, B, n):
     from whisper_vits_svc_b200 import whisper_infer
     dims = dict(synth.WHISPER_LARGE_V2_DIMS, n_audio_state=state, n_audio_head=heads, n_audio_layer=layers)

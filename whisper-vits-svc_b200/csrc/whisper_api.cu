@@ -13,7 +13,9 @@
 namespace svcb {
 int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
                    int M, int N, int K, int epi, cudaStream_t s);
-int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, cudaStream_t s);
+int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
+                             cudaStream_t s);
+int launch_rowmajor_to_image(const void* src, void* dst, int R, int K, int rows, cudaStream_t s);
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
                    cudaStream_t s);
 struct WBlock {
@@ -45,10 +47,11 @@ static WLayout whisper_layout(const svcb_whisper_config& c, int B, int n) {
   size_t off = 0;
   L.h1 = off; off = align256(off + (size_t)B * D * n * 4);
   L.x = off; off = align256(off + (size_t)L.M * D * 4);
-  L.a = off; off = align256(off + (size_t)L.M * D * 2);
+  const size_t Mp = (size_t)(L.M + 127) / 128 * 128;  // tile images are padded to whole 128-row tiles
+  L.a = off; off = align256(off + Mp * D * 2);
   L.qkv = off; off = align256(off + (size_t)L.M * 3 * D * 2);
-  L.att = off; off = align256(off + (size_t)L.M * D * 2);
-  L.mid = off; off = align256(off + (size_t)L.M * 4 * D * 2);
+  L.att = off; off = align256(off + Mp * D * 2);
+  L.mid = off; off = align256(off + Mp * 4 * D * 2);
   L.total = off + 4096;
   return L;
 }
@@ -60,8 +63,8 @@ int svcb_whisper_create(const void* dev_blob, size_t blob_bytes, const svcb_tens
   if (!dev_blob || !table_host || !cfg_host || !out) { set_error("null argument"); return SVCB_E_BAD_SHAPE; }
   if (((uintptr_t)dev_blob & 255) != 0) { set_error("weight blob must be 256-byte aligned"); return SVCB_E_BAD_ALIGN; }
   const svcb_whisper_config& c = *cfg_host;
-  if (c.n_state % 128 || c.n_state / c.n_head != 64 || c.n_layer < 1 || c.n_state > 2048) {
-    set_error("whisper config: n_state must be a multiple of 128 (<= 2048) with 64-wide heads");
+  if (c.n_state % 256 || c.n_state / c.n_head != 64 || c.n_layer < 1 || c.n_state > 2048) {
+    set_error("whisper config: n_state must be a multiple of 256 (<= 2048) with 64-wide heads");
     return SVCB_E_UNSUPPORTED;
   }
   int dev = 0;
@@ -151,7 +154,7 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
     const WBlock& b = w->blocks[i];
     SVCB_TRY(launch_ln_rows(x, b.ln1g, b.ln1b, a, M, D, true, s));
     SVCB_TRY(launch_gemm_tc(a, b.wqkv, b.bqkv, qkv, nullptr, M, 3 * D, D, 0, s));
-    SVCB_TRY(launch_whisper_attention(qkv, att, B, n2, D, c.n_head, s));
+    SVCB_TRY(launch_whisper_attention(qkv, att, B, n2, D, c.n_head, 1, s));
     SVCB_TRY(launch_gemm_tc(att, b.wo, b.bo, x, x, M, D, D, 2, s));
     SVCB_TRY(launch_ln_rows(x, b.ln2g, b.ln2b, a, M, D, true, s));
     SVCB_TRY(launch_gemm_tc(a, b.w1, b.b1, mid, nullptr, M, 4 * D, D, 1, s));
@@ -161,14 +164,26 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
 }
 
 
+size_t svcb_op_gemm_bf16_scratch_bytes(int32_t M, int32_t N, int32_t K) {
+  return ((size_t)(M + 127) / 128 * 128 * K + (size_t)N * K) * 2 + 1024;
+}
+
 int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
-                      int32_t M, int32_t N, int32_t K, int32_t epilogue, svcb_stream stream) {
-  return launch_gemm_tc(A_bf16, W_bf16, bias, out, res, M, N, K, epilogue, static_cast<cudaStream_t>(stream));
+                      int32_t M, int32_t N, int32_t K, int32_t epilogue, void* scratch, size_t scratch_bytes,
+                      svcb_stream stream) {
+  // row-major operands in, converted to tile images in `scratch`; epilogue 1 writes the tile image of out
+  if (!scratch || scratch_bytes < svcb_op_gemm_bf16_scratch_bytes(M, N, K)) { set_error("gemm scratch too small"); return SVCB_E_WORKSPACE; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* a_img = static_cast<char*>(scratch);
+  char* w_img = a_img + (((size_t)(M + 127) / 128 * 128 * K * 2 + 255) & ~(size_t)255);
+  SVCB_TRY(launch_rowmajor_to_image(A_bf16, a_img, M, K, 128, s));
+  SVCB_TRY(launch_rowmajor_to_image(W_bf16, w_img, N, K, 256, s));
+  return launch_gemm_tc(a_img, w_img, bias, out, res, M, N, K, epilogue, s);
 }
 
 int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
                            svcb_stream stream) {
-  return launch_whisper_attention(qkv_bf16, out_bf16, B, T, D, heads, static_cast<cudaStream_t>(stream));
+  return launch_whisper_attention(qkv_bf16, out_bf16, B, T, D, heads, 0, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

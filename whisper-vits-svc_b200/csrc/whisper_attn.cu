@@ -39,9 +39,15 @@ __device__ __forceinline__ void cp16(uint32_t dst, const void* src, bool valid) 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
 
-// qkv: bf16 [B*T, 3*D] rows = (q | k | v), out: bf16 [B*T, D]
+__device__ __forceinline__ size_t gemm_img_off(int m, int k, int KT) {  // = whisper_gemm.cu:img_off
+  return ((size_t)(m >> 7) * KT + (k >> 6)) * 8192 + (size_t)((k & 63) >> 3) * 1024 + (m & 127) * 8 + (k & 7);
+}
+
+// qkv: bf16 [B*T, 3*D] rows = (q | k | v); out: bf16 [B*T, D] row-major, or (img != 0) the GEMM tile
+// image of the same matrix (A operand of the out-projection)
 __global__ void __launch_bounds__(128)
-whisper_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int D) {
+whisper_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int T, int D,
+                         int img) {
   __shared__ __align__(128) uint8_t sQ[FA_BQ * 128];
   __shared__ __align__(128) uint8_t sKV[2][2][FA_BK * 128];  // [stage][k|v]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -165,22 +171,32 @@ whisper_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* _
   // ---- normalise and store
   const float inv0 = 1.f / l_run[0], inv1 = 1.f / l_run[1];
   const int r0 = q0 + warp * 16 + g, r1 = r0 + 8;
-  __nv_bfloat16* ob = out + (size_t)b * T * D + (size_t)h * FA_D;
+  if (img) {
+    const int KT = D / 64;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int col = 8 * j + 2 * t4;
-    if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + col) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
-    if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + col) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+    for (int j = 0; j < 8; ++j) {
+      const int col = h * FA_D + 8 * j + 2 * t4;
+      if (r0 < T) *reinterpret_cast<uint32_t*>(out + gemm_img_off(b * T + r0, col, KT)) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(out + gemm_img_off(b * T + r1, col, KT)) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+    }
+  } else {
+    __nv_bfloat16* ob = out + (size_t)b * T * D + (size_t)h * FA_D;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int col = 8 * j + 2 * t4;
+      if (r0 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r0 * D + col) = pack_bf16(o[j][0] * inv0, o[j][1] * inv0);
+      if (r1 < T) *reinterpret_cast<uint32_t*>(ob + (size_t)r1 * D + col) = pack_bf16(o[j][2] * inv1, o[j][3] * inv1);
+    }
   }
 }
 
-int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads,
+int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
                              cudaStream_t s) {
   if (D % heads || D / heads != FA_D) { set_error("whisper_attention: head dim must be 64"); return SVCB_E_UNSUPPORTED; }
   dim3 grid((T + FA_BQ - 1) / FA_BQ, heads, B);
   KernelScope ks("whisper_attention", s, 4.0 * B * heads * (double)T * T * FA_D, 2.0 * 4.0 * B * (double)T * D);
   whisper_attention_kernel<<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(qkv_bf16),
-                                                static_cast<__nv_bfloat16*>(out_bf16), T, D);
+                                                static_cast<__nv_bfloat16*>(out_bf16), T, D, img);
   SVCB_LAUNCH_CHECK("whisper_attention");
   return SVCB_OK;
 }
@@ -228,9 +244,9 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
       const float o0 = (v[i].x - mean) * rstd * gm.x + bt.x, o1 = (v[i].y - mean) * rstd * gm.y + bt.y;
       const float o2 = (v[i].z - mean) * rstd * gm.z + bt.z, o3 = (v[i].w - mean) * rstd * gm.w + bt.w;
-      if (OUT_BF16) {
+      if (OUT_BF16) {  // GEMM tile image (A operand of the following linear layer)
         uint2 pk = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
-        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + (size_t)row * D + c0) = pk;
+        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + gemm_img_off(row, c0, D / 64)) = pk;
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(y) + (size_t)row * D + c0) = make_float4(o0, o1, o2, o3);
       }

@@ -1,197 +1,221 @@
 // Dense bf16 GEMM on tcgen05/TMEM for the Whisper encoder's linear layers, with fused epilogues.
 //
-//   C[M,N] = A[M,K] . W[N,K]^T + bias            A = LayerNorm output / attention output (bf16)
-//                                               W = nn.Linear weight (bf16, [out,in] as stored)
-// Replaces the F.linear calls of whisper/model.py:66-82 (query/key/value/out) and :116
-// (mlp = Linear -> GELU -> Linear) including their bias, GELU and residual adds.
+//   C[M,N] = A[M,K] . W[N,K]^T + bias        replaces the F.linear calls of whisper/model.py:66-82
+//                                            (query/key/value/out) and :116 (Linear -> GELU -> Linear)
+//                                            including bias, GELU and the residual adds.
 //
-// One CTA = one 128 x BN output tile.  Four producer warps stream A/W k-tiles (64 wide) into a
-// STAGES-deep ring with 16-byte cp.async, scattering each K-chunk into the K-major panel layout of
-// tc.cuh; completion is published with cp.async.wait_group + fence.proxy.async + mbarrier.arrive.
-// One thread issues tcgen05.mma (M=128, N=BN, K=16 x4 per tile) and frees slots with
-// tcgen05.commit.  The producer warps then become the epilogue: tcgen05.ld -> bias / GELU /
-// residual -> vector stores.
+// Operands live in HBM as *tile images*: A (activations, written by the producing kernels) and W
+// (packed by the host) are stored tile by tile — [row-tile][k-tile] blocks of 128 (or BN) rows x 64
+// k, each block already in the K-major panel order of tc.cuh ([k/8][row][8]).  A k-tile of either
+// operand is therefore ONE contiguous bulk copy (TMA engine) signalled on an mbarrier: no tensor
+// maps, no swizzle bookkeeping, no LSU traffic (a first version gathered 16-byte chunks with
+// cp.async from row-major operands and reached 199 TFLOP/s; profiles/r01_notes.md).
+//
+// Persistent CTAs walk (m-tile, n-tile) pairs; three roles pipeline across tiles:
+//   producer thread   4-deep ring of (A 16 KB + W BN*128 B) k-tiles
+//   MMA thread        tcgen05.mma M=128, N=BN, K=16 x4 per k-tile into TMEM accumulator (tile & 1)
+//   8 epilogue warps  previous tile: tcgen05.ld -> bias / GELU / residual -> stores (row-major bf16,
+//                     tile-image bf16 for the next GEMM, or fp32 residual stream)
+#include <algorithm>
+
 #include "common.cuh"
 #include "tc.cuh"
 
 namespace svcb {
 
-enum GemmEpi : int { EPI_BF16 = 0, EPI_GELU_BF16 = 1, EPI_RESID_F32 = 2 };
+enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2 };
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
-  const uint32_t d = tc::smem_u32(dst);
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
+
+// element offset of (m, k) inside a tile image with KT k-tiles per row-tile
+__host__ __device__ inline size_t img_off(int m, int k, int KT) {
+  return ((size_t)(m >> 7) * KT + (k >> 6)) * (GM_BM * GM_BK) + (size_t)((k & 63) >> 3) * (GM_BM * 8) + (m & 127) * 8 + (k & 7);
 }
 
 template <int BN, int EPI>
-__global__ void __launch_bounds__(160, 1)
-gemm_tc_kernel(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ W,
+__global__ void __launch_bounds__(320, 1)
+gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __restrict__ Wimg,
                const float* __restrict__ bias, void* out, const float* res, int M, int N, int K) {
-  constexpr int BM = 128, BK = 64, KC = BK / 8;
-  constexpr int STAGES = BN == 256 ? 4 : 4;
-  constexpr uint32_t A_BYTES = BM * BK * 2, B_BYTES = BN * BK * 2, ST_BYTES = A_BYTES + B_BYTES;
+  constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, ST_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_full[STAGES], bar_empty[STAGES], bar_acc;
+  __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  const int nk = K / BK;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int KT = K / GM_BK, NT = N / BN, MT = (M + GM_BM - 1) / GM_BM;
+  const int ntiles = MT * NT;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&bar_full[s], 128); tc::mbar_init(&bar_empty[s], 1); }
-    tc::mbar_init(&bar_acc, 1);
+    for (int s = 0; s < GM_STAGES; ++s) { tc::mbar_init(&bar_full[s], 1); tc::mbar_init(&bar_empty[s], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 256); }
     tc::fence_barrier_init();
   }
   __syncwarp();
-  if (warp == 4) tc::tmem_alloc(&tmem_slot, BN);
+  if (warp == 8) tc::tmem_alloc(&tmem_slot, 2 * BN <= 256 ? 256 : 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (tid < 128) {
-    // ------------------------------------------------------------------ producers
-    auto issue = [&](int st, int kt) {
-      uint8_t* As = smem + (size_t)st * ST_BYTES;
-      uint8_t* Bs = As + A_BYTES;
-      const int k0 = kt * BK;
-#pragma unroll
-      for (int i = 0; i < (BM * KC) / 128; ++i) {
-        const int c = tid + 128 * i;
-        const int r = (c & 7) + 8 * ((c >> 5) & 15), kc = ((c >> 3) & 3) + 4 * (c >> 9);
-        const int gm = m0 + r;
-        const bool ok = gm < M;
-        cp_async16(As + ((size_t)kc * BM + r) * 16, A + (size_t)(ok ? gm : 0) * K + k0 + kc * 8, ok);
+  if (tid == 256) {
+    // ------------------------------------------------------------------ producer
+    int kc = 0;  // global k-tile counter (ring position)
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int mt = tile / NT, nt = tile - mt * NT;
+      const __nv_bfloat16* a_src = Aimg + (size_t)mt * KT * (GM_BM * GM_BK);
+      const __nv_bfloat16* w_src = Wimg + (size_t)nt * KT * (BN * GM_BK);
+      for (int kt = 0; kt < KT; ++kt, ++kc) {
+        const int st = kc % GM_STAGES;
+        if (kc >= GM_STAGES) tc::mbar_wait(&bar_empty[st], (uint32_t)(((kc / GM_STAGES) - 1) & 1));
+        uint8_t* As = smem + (size_t)st * ST_BYTES;
+        tc::mbar_arrive_expect_tx(&bar_full[st], ST_BYTES);
+        tc::bulk_g2s(As, a_src + (size_t)kt * (GM_BM * GM_BK), A_BYTES, &bar_full[st]);
+        tc::bulk_g2s(As + A_BYTES, w_src + (size_t)kt * (BN * GM_BK), B_BYTES, &bar_full[st]);
       }
-#pragma unroll
-      for (int i = 0; i < (BN * KC) / 128; ++i) {
-        const int c = tid + 128 * i;
-        constexpr int RH = BN / 8;  // row groups of 8
-        const int r = (c & 7) + 8 * ((c >> 5) % RH), kc = ((c >> 3) & 3) + 4 * ((c >> 5) / RH);
-        cp_async16(Bs + ((size_t)kc * BN + r) * 16, W + (size_t)(n0 + r) * K + k0 + kc * 8, true);
-      }
-    };
-    for (int s = 0; s < STAGES - 1; ++s) {
-      if (s < nk) issue(s, s);
-      cp_async_commit();
     }
-    for (int kt = 0; kt < nk; ++kt) {
-      const int nxt = kt + STAGES - 1;
-      if (nxt < nk) {
-        const int st = nxt % STAGES;
-        if (nxt >= STAGES) tc::mbar_wait(&bar_empty[st], (uint32_t)(((nxt / STAGES) - 1) & 1));
-        issue(st, nxt);
+  } else if (tid == 288) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = tc::idesc_bf16(GM_BM, BN);
+    const uint32_t s0 = tc::smem_u32(smem);
+    const uint32_t lbo_a = GM_BM * 16u, lbo_b = BN * 16u;
+    const uint32_t kstep_a = (2u * lbo_a) >> 4, kstep_b = (2u * lbo_b) >> 4;
+    int kc = 0, it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      if (it >= 2) tc::mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) - 1) & 1));
+      tc::fence_after_sync();
+      const uint32_t d_tmem = tmem + (uint32_t)(acc * BN);
+      for (int kt = 0; kt < KT; ++kt, ++kc) {
+        const int st = kc % GM_STAGES;
+        tc::mbar_wait(&bar_full[st], (uint32_t)((kc / GM_STAGES) & 1));
+        tc::fence_after_sync();
+        const uint32_t a0 = s0 + (uint32_t)st * ST_BYTES;
+        uint64_t ad = tc::smem_desc(a0, lbo_a), bd = tc::smem_desc(a0 + A_BYTES, lbo_b);
+#pragma unroll
+        for (int kk = 0; kk < GM_BK / 16; ++kk) {
+          tc::mma_bf16(d_tmem, ad, bd, idesc, (kt | kk) ? 1u : 0u);
+          ad += kstep_a; bd += kstep_b;
+        }
+        tc::mma_commit(&bar_empty[st]);
       }
-      cp_async_commit();
-      cp_async_wait<STAGES - 1>();
-      tc::fence_proxy_async_smem();
-      mbar_arrive(&bar_full[kt % STAGES]);
+      tc::mma_commit(&t_full[acc]);
     }
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue
-    tc::mbar_wait(&bar_acc, 0);
-    tc::fence_after_sync();
-    const int m = m0 + tid;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      tc::tmem_ld_wait();
-      if (m < M) {
-        float f[16];
+    const int grp = warp >> 2, wq = warp & 3;  // two warp groups split the columns
+    int it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      const int mt = tile / NT, nt = tile - mt * NT;
+      tc::mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      tc::fence_after_sync();
+      const int m = mt * GM_BM + wq * 32 + lane;
+      const int n0 = nt * BN;
+      const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * BN);
+      for (int c0 = grp * (BN / 2); c0 < (grp + 1) * (BN / 2); c0 += 16) {
+        uint32_t v[16];
+        tc::tmem_ld16(tbase + (uint32_t)c0, v);
+        float r16[16];
+        if (EPI == EPI_RESID_F32 && m < M) {
+          const float4* rr = reinterpret_cast<const float4*>(res + (size_t)m * N + n0 + c0);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-        const size_t off = (size_t)m * N + n0 + c0;
-        if (EPI == EPI_RESID_F32) {
-          float* o = static_cast<float*>(out) + off;
-          const float* rr = res + off;
+          for (int j = 0; j < 4; ++j) { const float4 q = rr[j]; r16[4 * j] = q.x; r16[4 * j + 1] = q.y; r16[4 * j + 2] = q.z; r16[4 * j + 3] = q.w; }
+        }
+        tc::tmem_ld_wait();
+        if (m < M) {
+          float f[16];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 r4 = *reinterpret_cast<const float4*>(rr + j);
-            float4 o4 = make_float4(f[j] + r4.x, f[j + 1] + r4.y, f[j + 2] + r4.z, f[j + 3] + r4.w);
-            *reinterpret_cast<float4*>(o + j) = o4;
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
+          if (EPI == EPI_RESID_F32) {
+            float* o = static_cast<float*>(out) + (size_t)m * N + n0 + c0;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(f[j] + r16[j], f[j + 1] + r16[j + 1], f[j + 2] + r16[j + 2], f[j + 3] + r16[j + 3]);
+          } else {
+            __align__(16) __nv_bfloat16 h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float x = f[j];
+              if (EPI == EPI_GELU_BF16_IMAGE) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+              h[j] = __float2bfloat16_rn(x);
+            }
+            if (EPI == EPI_GELU_BF16_IMAGE) {  // A operand of the next GEMM (its K = this N)
+              __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+              *reinterpret_cast<uint4*>(ob + img_off(m, n0 + c0, N / GM_BK)) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(ob + img_off(m, n0 + c0 + 8, N / GM_BK)) = *reinterpret_cast<const uint4*>(h + 8);
+            } else {
+              __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + (size_t)m * N + n0 + c0;
+              *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(h + 8);
+            }
           }
-        } else {
-          __align__(16) __nv_bfloat16 h[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = f[j];
-            if (EPI == EPI_GELU_BF16) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-            h[j] = __float2bfloat16_rn(x);
-          }
-          __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out) + off;
-          *reinterpret_cast<uint4*>(o) = *reinterpret_cast<const uint4*>(h);
-          *reinterpret_cast<uint4*>(o + 8) = *reinterpret_cast<const uint4*>(h + 8);
         }
       }
+      tc::fence_before_sync();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&t_empty[acc])) : "memory");
     }
-  } else if (tid == 128) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = tc::idesc_bf16(BM, BN);
-    const uint32_t s0 = tc::smem_u32(smem);
-    for (int kt = 0; kt < nk; ++kt) {
-      const int st = kt % STAGES;
-      tc::mbar_wait(&bar_full[st], (uint32_t)((kt / STAGES) & 1));
-      tc::fence_after_sync();
-      const uint32_t a0 = s0 + (uint32_t)st * ST_BYTES, b0 = a0 + A_BYTES;
-#pragma unroll
-      for (int kk = 0; kk < BK / 16; ++kk) {
-        const uint64_t ad = tc::smem_desc(a0 + (uint32_t)kk * 2u * BM * 16u, BM * 16u);
-        const uint64_t bd = tc::smem_desc(b0 + (uint32_t)kk * 2u * BN * 16u, BN * 16u);
-        tc::mma_bf16(tmem, ad, bd, idesc, (kt | kk) ? 1u : 0u);
-      }
-      tc::mma_commit(&bar_empty[st]);
-    }
-    tc::mma_commit(&bar_acc);
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, BN);
+  if (warp == 8) tc::tmem_dealloc(tmem, 2 * BN <= 256 ? 256 : 512);
 }
 
 template <int BN, int EPI>
 static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, void* out,
                          const float* res, int M, int N, int K, cudaStream_t s) {
-  constexpr size_t smem = (size_t)4 * (128 * 64 * 2 + BN * 64 * 2);
+  constexpr size_t smem = (size_t)GM_STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2);
   static bool attr = false;
+  static int n_sm = 0;
   if (!attr) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem));
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    SVCB_CUDA_CHECK(cudaGetDevice(&dev));
+    SVCB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
     attr = true;
   }
-  dim3 grid(N / BN, (M + 127) / 128);
+  const int ntiles = ((M + GM_BM - 1) / GM_BM) * (N / BN);
+  const int grid = std::min(ntiles, n_sm);
   KernelScope ks("whisper_gemm_tc", s, 2.0 * M * (double)N * K,
                  2.0 * ((double)M * K + (double)N * K) + (EPI == EPI_RESID_F32 ? 8.0 : 2.0) * M * (double)N);
-  gemm_tc_kernel<BN, EPI><<<grid, 160, smem, s>>>(A, W, bias, out, res, M, N, K);
+  gemm_tc_kernel<BN, EPI><<<grid, 320, smem, s>>>(A, W, bias, out, res, M, N, K);
   SVCB_LAUNCH_CHECK("gemm_tc");
   return SVCB_OK;
 }
 
-int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
+// A_img: tile image [ceil(M/128)][K/64][8][128][8]; W_img: tile image [N/256][K/64][8][256][8]
+int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, const float* res,
                    int M, int N, int K, int epi, cudaStream_t s) {
   if (M <= 0) return SVCB_OK;
-  if (K % 64 || N % 128) { set_error("gemm_tc: need K % 64 == 0 and N % 128 == 0"); return SVCB_E_BAD_SHAPE; }
-  const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(A_bf16);
-  const __nv_bfloat16* W = static_cast<const __nv_bfloat16*>(W_bf16);
-  const bool wide = (N % 256 == 0);
+  if (K % 64 || N % 256) { set_error("gemm_tc: need K % 64 == 0 and N % 256 == 0"); return SVCB_E_BAD_SHAPE; }
+  const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(A_img);
+  const __nv_bfloat16* W = static_cast<const __nv_bfloat16*>(W_img);
   switch (epi) {
-    case EPI_BF16:
-      return wide ? launch_gemm_t<256, EPI_BF16>(A, W, bias, out, res, M, N, K, s)
-                  : launch_gemm_t<128, EPI_BF16>(A, W, bias, out, res, M, N, K, s);
-    case EPI_GELU_BF16:
-      return wide ? launch_gemm_t<256, EPI_GELU_BF16>(A, W, bias, out, res, M, N, K, s)
-                  : launch_gemm_t<128, EPI_GELU_BF16>(A, W, bias, out, res, M, N, K, s);
-    case EPI_RESID_F32:
-      return wide ? launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, s)
-                  : launch_gemm_t<128, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, s);
+    case EPI_BF16_ROWMAJOR: return launch_gemm_t<256, EPI_BF16_ROWMAJOR>(A, W, bias, out, res, M, N, K, s);
+    case EPI_GELU_BF16_IMAGE: return launch_gemm_t<256, EPI_GELU_BF16_IMAGE>(A, W, bias, out, res, M, N, K, s);
+    case EPI_RESID_F32: return launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, s);
   }
   set_error("gemm_tc: unknown epilogue");
   return SVCB_E_BAD_SHAPE;
+}
+
+// row-major bf16 [R,K] -> tile image with `rows` rows per tile (128 for A, 256 for W); used by the
+// unit-test entry point — the encoder's kernels write A images directly and the host packs W.
+__global__ void rowmajor_to_image_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                         int R, int K, int rows) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // one 16-byte chunk each
+  const int kc_per_row = K / 8;
+  if (idx >= (size_t)R * kc_per_row) return;
+  const int m = (int)(idx / kc_per_row), k = (int)(idx % kc_per_row) * 8;
+  const size_t off = ((size_t)(m / rows) * (K / GM_BK) + (k >> 6)) * ((size_t)rows * GM_BK) +
+                     (size_t)((k & 63) >> 3) * (rows * 8) + (size_t)(m % rows) * 8;
+  *reinterpret_cast<uint4*>(dst + off) = *reinterpret_cast<const uint4*>(src + (size_t)m * K + k);
+}
+
+int launch_rowmajor_to_image(const void* src, void* dst, int R, int K, int rows, cudaStream_t s) {
+  const size_t n = (size_t)R * (K / 8);
+  rowmajor_to_image_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(static_cast<const __nv_bfloat16*>(src),
+                                                                       static_cast<__nv_bfloat16*>(dst), R, K, rows);
+  SVCB_LAUNCH_CHECK("rowmajor_to_image");
+  return SVCB_OK;
 }
 
 }  // namespace svcb

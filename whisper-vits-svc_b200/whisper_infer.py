@@ -32,7 +32,14 @@ HOP_LENGTH = 160
 
 # ------------------------------------------------------------------------------ packing
 def _bf16_as_f32(w: torch.Tensor) -> torch.Tensor:
-    return w.detach().float().contiguous().bfloat16().view(torch.float32).reshape(-1)
+    """nn.Linear weight [N, K] -> bf16 GEMM tile image [N/256][K/64][8][256][8] (csrc/whisper_gemm.cu:
+    one (n-tile, k-tile) block = one contiguous bulk copy in the K-major panel order), returned as a
+    float32 view of the bytes."""
+    w = w.detach().float().contiguous().bfloat16()
+    n, k = w.shape
+    assert n % 256 == 0 and k % 64 == 0, (n, k)
+    img = w.view(n // 256, 256, k // 64, 8, 8).permute(0, 2, 3, 1, 4).contiguous()  # nt, kt, kc, row, e
+    return img.view(torch.float32).reshape(-1)
 
 
 def sinusoids(length: int, channels: int, max_timescale: float = 10000.0) -> torch.Tensor:
