@@ -34,9 +34,12 @@ __host__ __device__ inline int ab_halo(int K, const int* dil) {
 template <int C>
 struct AbCfg {
   static constexpr int CP = (C + 3) / 4 * 4;
-  static constexpr int TOUT = C <= 10 ? 1024 : 512;
-  static constexpr int THREADS = C <= 10 ? 1024 : 512;   // 32 warps when the register budget allows
+  // The buffer width W (tile + both halos) is fixed so that the convolution's NT*THREADS time slots
+  // are exactly filled (a 1216-wide buffer on 2x512 slots wasted 40 % of the FMA issue, r01 profile);
+  // the number of output samples per CTA follows from the block's receptive field: TOUT = W - 2H.
+  static constexpr int THREADS = C <= 10 ? 512 : 384;
   static constexpr int NT = 2;                           // time steps per thread in the convolution
+  static constexpr int W = NT * THREADS;                 // 1024 (C=10) / 768 (C=20)
 };
 
 // SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
@@ -174,15 +177,15 @@ __global__ void __launch_bounds__(AbCfg<C>::THREADS, 1)
 amp_block_fused_kernel(const AmpBlockParams p) {
   constexpr int AB_THREADS = AbCfg<C>::THREADS;
   constexpr int CP = AbCfg<C>::CP;
-  constexpr int TOUT = AbCfg<C>::TOUT;
+  constexpr int W = AbCfg<C>::W;
   extern __shared__ __align__(16) float ab_smem[];
   __shared__ float f_up[12], f_dn[12], s_ea[C], s_ib[C], s_bias[CP];
   const int tid = threadIdx.x;
   const int b = blockIdx.y;
-  const int t0 = blockIdx.x * TOUT;
   const int H = ab_halo(K, p.dil);
-  const int W = TOUT + 2 * H;
-  const int WS = W + 2 * AB_GUARD;
+  const int TOUT = W - 2 * H;
+  const int t0 = blockIdx.x * TOUT;
+  constexpr int WS = W + 2 * AB_GUARD;
   float* X = ab_smem;
   float* Y = X + C * WS;
   float* Z = Y + C * WS;
@@ -247,7 +250,8 @@ template <int C, int K>
 static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   constexpr int AB_THREADS = AbCfg<C>::THREADS;
   const int H = ab_halo(p.K, p.dil);
-  const int W = AbCfg<C>::TOUT + 2 * H, WS = W + 2 * AB_GUARD;
+  const int W = AbCfg<C>::W, WS = W + 2 * AB_GUARD, TOUT = W - 2 * H;
+  if (TOUT < 64) { set_error("amp_block_fused: receptive field too large for the tile"); return SVCB_E_UNSUPPORTED; }
   const size_t smem = ((size_t)3 * C * WS + (AB_THREADS / 32) * AB_VSL + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
   if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;
@@ -255,7 +259,7 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
     SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
-  dim3 grid((p.L + AbCfg<C>::TOUT - 1) / AbCfg<C>::TOUT, p.B);
+  dim3 grid((p.L + TOUT - 1) / TOUT, p.B);
   char kname[64];
   snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);
   KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B + 6 * 70.0 * C * (double)p.L * p.B,
