@@ -385,6 +385,8 @@ static AmpPlan amp_plan(int Cp, int K, int dil, int nsplit) {
   AmpPlan pl;
   pl.acc_stride = (Cp + 31) / 32 * 32;
   pl.ncols = (int)tc_cols_host(2 * pl.acc_stride);
+  // Measured (r01): resident weights + 2 A buffers (one CTA per SM) beat streaming weights with two
+  // CTAs per SM on the C=40/80 stages (33.0 vs 37.1 ms per step), so residency is preferred.
   if (2 * a_buf + nch * wb + 128 <= limit) { pl.resident = 1; pl.nabuf = 2; pl.smem = 2 * a_buf + nch * wb + 128; }
   else if (2 * a_buf + 2 * wb + 128 <= limit) { pl.resident = 0; pl.nabuf = 2; pl.smem = 2 * a_buf + 2 * wb + 128; }
   else { pl.resident = 0; pl.nabuf = 1; pl.smem = a_buf + 2 * wb + 128; }

@@ -465,7 +465,19 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
       p.out_mul = 1; p.out_off = -p.q0;
       fp.tmp[r] = p.y; fp.nq[r] = p.nq; fp.q0[r] = p.q0;
       slab += (size_t)B * chn * p.nq;
-      RUN(launch_conv1d(p, s));
+      if (c.precision != 0 && us.phase[r].tc && p.nq == L && us.taps - 1 - p.q0 >= 0) {
+        // phase r is a stride-1 convolution with nq == L outputs: x index = t + j - (taps-1-q0)
+        ConvTcParams q;
+        const ConvW& w = us.phase[r];
+        q.x = x; q.sxb = (long long)ch * L; q.sxc = L; q.sxt = 1;
+        q.wpk = w.tc; q.bias = nullptr; q.y = p.y;
+        q.B = B; q.Cin = ch; q.cin_pad = w.cin_pad; q.Cout = chn; q.Tin = L; q.Tout = L;
+        q.K = us.taps; q.dil = 1; q.pad = us.taps - 1 - p.q0; q.kch = w.kch; q.bn = w.bn; q.ntiles = w.ntiles;
+        q.nsplit = c.precision == 1 ? 1 : 3;
+        RUN(launch_conv_tc(q, s));
+      } else {
+        RUN(launch_conv1d(p, s));
+      }
     }
     if (!ctx.dry) SVCB_TRY(launch_ups_finalize(fp, B, s));
     if (!fuse_noise) {  // long noise filters (K = 2*prod(later rates)): separate accumulate pass
@@ -580,7 +592,7 @@ static int resolve(svcb_model* m) {
     m->hop *= us.rate;
     const std::string p = "dec.ups." + std::to_string(i);
     for (int r = 0; r < us.rate; ++r)
-      us.phase.push_back(R.conv(p + ".ph" + std::to_string(r), ch, ch / 2, us.taps, false));
+      us.phase.push_back(R.conv(p + ".ph" + std::to_string(r), ch, ch / 2, us.taps, false, true));
     us.bias = R.get(p + ".b", ch / 2);
     ch /= 2;
   }

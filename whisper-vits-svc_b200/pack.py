@@ -174,6 +174,7 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
                 if j < k:
                     sub[:, :, jp] = w[:, :, j].t()
             put(f"dec.ups.{i}.ph{r}.w", pack_conv(sub))
+            put(f"dec.ups.{i}.ph{r}.tc", pack_conv_tc_general(sub))
         put(f"dec.ups.{i}.b", sd[f"dec.ups.{i}.bias"])
         conv(f"dec.noise.{i}", sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"])
     n_blocks = cfg["n_ups"] * cfg["n_res"]
