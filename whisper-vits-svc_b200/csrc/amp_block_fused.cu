@@ -46,7 +46,7 @@ struct AbCfg {
 // index inside the sequence.  Warp-private: a warp takes (channel, 64-output chunk) items, builds the
 // 2x-rate Snake values of its chunk in its own scratch slice and decimates them — only __syncwarp,
 // no CTA barrier inside the activation.
-constexpr int AB_CH = 64;
+constexpr int AB_CH = 58;   // outputs per item: 58 + 6 = 64 up-sampling positions = two full warp passes
 constexpr int AB_VSL = 2 * (AB_CH + 6) + 4;  // scratch floats per warp (slot 0 unused: tap 0 lands on an even index)
 
 template <int C>
@@ -65,10 +65,14 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
     const int c = item / nchunks, n0 = (item - c * nchunks) * AB_CH;
     const float* xr = src + c * WS + AB_GUARD;
     const float a_ = ea[c], b_ = ib[c];
-    for (int ai = lane; ai < AB_CH + 6; ai += 32) {
+    // chunk-uniform: does any tap of this chunk leave the sequence (replicate padding needed)?
+    const bool interior = (n0 - 6 >= lo_i) && (n0 + AB_CH + 5 <= hi_i);
+#pragma unroll
+    for (int pass = 0; pass < (AB_CH + 6) / 32; ++pass) {
+      const int ai = lane + 32 * pass;
       const int a = n0 - 3 + ai;
       float x[7];
-      if (a - 3 >= lo_i && a + 3 <= hi_i) {
+      if (interior) {
 #pragma unroll
         for (int d = 0; d < 7; ++d) x[d] = xr[a - 3 + d];
       } else {
@@ -133,6 +137,7 @@ __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __
 #pragma unroll
       for (int co = 0; co < CP; ++co) acc[i][co] = co < C ? bsm[co] : 0.f;
     }
+#pragma unroll 2
     for (int ci = 0; ci < C; ++ci) {
       const float* sr = src + ci * WS;
       const float* wr = wsm + ci * K * CP;

@@ -15,6 +15,8 @@
 //   descriptor; tcgen05.commit releases W slots and A buffers.
 // * Epilogue (the producer warps again): tcgen05.ld -> bias -> {none, ReLU, Mish, tanh, WaveNet
 //   gate on interleaved channel pairs} -> output mask -> residual -> accumulate -> store [B,C,T].
+#include <cstdio>
+
 #include "common.cuh"
 #include "tc.cuh"
 
@@ -244,7 +246,9 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
   }
   dim3 grid((p.Tout + CT_M - 1) / CT_M, p.ntiles, p.B);
   const int cout_real = (p.flags & CONV_GATE) ? p.Cout / 2 : p.Cout;
-  KernelScope ks(p.nsplit == 3 ? "conv_tc_bf16x3" : "conv_tc_bf16", s,
+  char kname[64];
+  snprintf(kname, sizeof(kname), "conv_tc_%s_%dto%d_k%d_o1", p.nsplit == 3 ? "bf16x3" : "bf16", p.Cin, p.Cout, p.K);
+  KernelScope ks(kname, s,
                  2.0 * p.Cin * p.K * p.Cout * (double)p.Tout * p.B,
                  4.0 * ((double)p.B * p.Cin * p.Tin + (double)p.B * cout_real * p.Tout * (p.res ? 2 : 1)) +
                      2.0 * (double)p.Cin * p.K * p.Cout);
