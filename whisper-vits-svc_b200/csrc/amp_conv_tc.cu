@@ -49,7 +49,7 @@ __device__ __forceinline__ float fast_sin(float x) {
 //  (c) one thread per pair of output rows: 14 consecutive v (4 x LDS.128) -> two 12-tap
 //      decimations per channel, bf16 hi/lo split, two 16-byte rows stored contiguously.
 // Only the first/last CTA of a sequence needs the replicate padding of v (fix-up pass).
-constexpr int SP_TL = 512;  // image rows per CTA
+constexpr int SP_TL = 506;  // image rows per CTA: 506 + 6 = 512 up-sampling positions = 2 exact passes of 256 threads
 constexpr int SP_XW = SP_TL + 12;
 constexpr int SP_VW = 2 * SP_TL + 16;
 
@@ -76,33 +76,30 @@ snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
   const int mbase = 2 * n0 - 5;
   if (any) {
     const float* xb = x + ((long long)b * C + oc * 8) * L;
-    for (int c = 0; c < nvalid; ++c) {
-      const float* xr = xb + (long long)c * L;
-      for (int i = tid; i < SP_XW; i += 256) {
-        const int g = min(max(n0 - 6 + i, 0), L - 1);
-        xs[c * SP_XW + i] = __ldg(xr + g);
-      }
+    for (int idx = tid; idx < nvalid * SP_XW; idx += 256) {   // flat over (channel, position)
+      const int c = idx / SP_XW, i = idx - c * SP_XW;
+      const int g = min(max(n0 - 6 + i, 0), L - 1);
+      xs[idx] = __ldg(xb + (long long)c * L + g);
     }
     __syncthreads();
-    for (int c = 0; c < nvalid; ++c) {
+    static_assert(SP_TL + 6 == 512, "phase (b) indexing assumes 512 up-sampling positions per channel");
+    for (int idx = tid; idx < nvalid * 512; idx += 256) {     // flat over (channel, a - n0 + 3)
+      const int c = idx >> 9, ar = (idx & 511) - 3;
       const float a_ = s_ea[c], ib = s_ib[c];
-      const float* xc = xs + c * SP_XW;
+      const float* xp = xs + c * SP_XW + ar + 6;
       float* vc = vs + c * SP_VW;
-      for (int ar = tid - 3; ar <= SP_TL + 2; ar += 256) {   // a - n0
-        const float* xp = xc + ar + 6;
-        const float xm3 = xp[-3], xm2 = xp[-2], xm1 = xp[-1], x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
-        float ue = xm3 * f_up[11];
-        ue = fmaf(xm2, f_up[9], ue); ue = fmaf(xm1, f_up[7], ue); ue = fmaf(x0, f_up[5], ue);
-        ue = fmaf(x1, f_up[3], ue); ue = fmaf(x2, f_up[1], ue);
-        float uo = xm2 * f_up[10];
-        uo = fmaf(xm1, f_up[8], uo); uo = fmaf(x0, f_up[6], uo); uo = fmaf(x1, f_up[4], uo);
-        uo = fmaf(x2, f_up[2], uo); uo = fmaf(x3, f_up[0], uo);
-        ue *= 2.f; uo *= 2.f;
-        const float se = __sinf(ue * a_), so = __sinf(uo * a_);
-        const int j = 2 * ar + 5;
-        if (j >= 0) vc[j] = fmaf(ib, se * se, ue);
-        vc[j + 1] = fmaf(ib, so * so, uo);
-      }
+      const float xm3 = xp[-3], xm2 = xp[-2], xm1 = xp[-1], x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
+      float ue = xm3 * f_up[11];
+      ue = fmaf(xm2, f_up[9], ue); ue = fmaf(xm1, f_up[7], ue); ue = fmaf(x0, f_up[5], ue);
+      ue = fmaf(x1, f_up[3], ue); ue = fmaf(x2, f_up[1], ue);
+      float uo = xm2 * f_up[10];
+      uo = fmaf(xm1, f_up[8], uo); uo = fmaf(x0, f_up[6], uo); uo = fmaf(x1, f_up[4], uo);
+      uo = fmaf(x2, f_up[2], uo); uo = fmaf(x3, f_up[0], uo);
+      ue *= 2.f; uo *= 2.f;
+      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
+      const int j = 2 * ar + 5;
+      if (j >= 0) vc[j] = fmaf(ib, se * se, ue);
+      vc[j + 1] = fmaf(ib, so * so, uo);
     }
     __syncthreads();
     if (mbase < 0 || mbase + 2 * SP_TL + 10 > 2 * L) {  // replicate padding of v at the sequence ends
@@ -121,7 +118,7 @@ snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, _
   {
     const int r = 2 * tid;
     const int row = row0 + r;
-    if (row < Lp) {
+    if (r < SP_TL && row < Lp) {
       const int tau = n0 + r;
       __align__(16) __nv_bfloat162 h2[8], l2[8];  // [row parity*4 + channel pair]
       float prev0 = 0.f, prev1 = 0.f;
