@@ -235,3 +235,15 @@ def test_svc_infer_chunk_loop_vs_oracle(model_tc, hp, sd, tmp_path):
     err = float(np.abs(out - ref).max())
     print(f"svc_infer 26 s utterance, 2 chunks: max-abs {err:.3e}")
     assert err <= 2e-4
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (2, 3), (1, 37)])
+def test_tiny_lengths_tensor_core_mode(model_tc, hp, sd, B, T):
+    """Sequences shorter than one tile in every stage (single CTA holds both sequence edges)."""
+    d = make_inputs(40 + T, B, T, hp)
+    src = O.pitch2source(sd, hp, d["pit"], d["rand_ini"], d["noise"])
+    wave = model_tc.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, eps=d["eps"])
+    wave_o = O.synthesizer_infer(sd, hp, d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, d["eps"])
+    err = max_abs(wave, wave_o)
+    print(f"B={B} T={T} (precision 3): wave max-abs err {err:.3e}")
+    assert err <= 2e-4

@@ -66,6 +66,7 @@ struct UpStage {
   std::vector<ConvW> phase;  // one sub-convolution per output phase
   const float* bias;
   ConvW noise;
+  ConvW noise_tc;            // long noise filter as a 2-tap conv over the space-to-depth source
   int rate, k, pad, taps;
 };
 struct ResBlock {
@@ -228,6 +229,17 @@ static int launch_ups_finalize(const UpsFinalizeParams& p, int B, cudaStream_t s
   ups_finalize_kernel<<<grid, 256, 0, s>>>(p);
   SVCB_LAUNCH_CHECK("ups_finalize");
   return SVCB_OK;
+}
+
+// source [B][Ltot] -> zero-padded copy [B][32 + Ltot + tail] for the space-to-depth noise convs
+constexpr int SRC_PADF = 32;
+__global__ void pad_source_kernel(const float* __restrict__ src, float* __restrict__ dst, long long Ltot,
+                                  long long Lpad) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.y;
+  if (i >= Lpad) return;
+  const long long si = i - SRC_PADF;
+  dst[(long long)b * Lpad + i] = (si >= 0 && si < Ltot) ? src[(long long)b * Ltot + si] : 0.f;
 }
 
 // ----------------------------------------------------------------------------- prior encoder
@@ -418,10 +430,18 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     int ch = c.gen_initial_channel; long long L = T;
     for (int i = 0; i < c.n_ups; ++i) { ch /= 2; L *= c.up_rates[i]; img_bytes = std::max<size_t>(img_bytes, p8_image_bytes(B, ch, (int)L)); }
   }
+  const long long Lpad = (SRC_PADF + Ltot + 128 + 3) / 4 * 4;
+  float* SRCP = c.precision != 0 ? ctx.alloc<float>((size_t)B * Lpad) : nullptr;
   void* IMG_HI = img_bytes ? ctx.alloc<uint8_t>(img_bytes) : nullptr;
   void* IMG_LO = (img_bytes && c.precision != 1) ? ctx.alloc<uint8_t>(img_bytes) : nullptr;
   SVCB_TRY(check_ws(ctx));
 
+  if (c.precision != 0 && !ctx.dry) {
+    dim3 grid((unsigned)((Lpad + 255) / 256), B);
+    KernelScope ks("pad_source", s, 0.0, 8.0 * B * (double)Lpad);
+    pad_source_kernel<<<grid, 256, 0, s>>>(source, SRCP, Ltot, Lpad);
+    SVCB_LAUNCH_CHECK("pad_source");
+  }
   RUN(launch_linear_small(spk, m->ad_sw, m->ad_sb, sc, B, c.spk_dim, U, s));
   RUN(launch_linear_small(spk, m->ad_bw, m->ad_bb, bi, B, c.spk_dim, U, s));
   RUN(launch_layernorm_c(z, nullptr, sc, bi, xa, B, U, T, U, 1e-5f, s));
@@ -480,7 +500,18 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
       }
     }
     if (!ctx.dry) SVCB_TRY(launch_ups_finalize(fp, B, s));
-    if (!fuse_noise) {  // long noise filters (K = 2*prod(later rates)): separate accumulate pass
+    if (!fuse_noise && c.precision != 0 && us.noise_tc.tc && sf <= 2 * SRC_PADF && !last) {
+      // long noise filter as Conv1d(sf -> C, K=2) over the space-to-depth view of the padded source:
+      // x[b, ci, t] = srcp[b][32 - sf/2 + sf*t + ci]
+      const ConvW& w = us.noise_tc;
+      ConvTcParams q;
+      q.x = SRCP + (SRC_PADF - sf / 2); q.sxb = Lpad; q.sxc = 1; q.sxt = sf;
+      q.wpk = w.tc; q.bias = w.b; q.y = X;
+      q.B = B; q.Cin = sf; q.cin_pad = w.cin_pad; q.Cout = chn; q.Tin = Ln + 1; q.Tout = Ln;
+      q.K = 2; q.dil = 1; q.pad = 0; q.kch = w.kch; q.bn = w.bn; q.ntiles = w.ntiles;
+      q.nsplit = c.precision == 1 ? 1 : 3; q.flags = CONV_ACCUM;
+      RUN(launch_conv_tc(q, s));
+    } else if (!fuse_noise) {  // long noise filters (K = 2*prod(later rates)): separate accumulate pass
       ConvParams p;
       p.x = source; p.sxb = Ltot; p.sxc = Ltot; p.sxt = 1;
       p.w = us.noise.w; p.cout_pad = us.noise.cout_pad; p.bias = us.noise.b;
@@ -602,6 +633,14 @@ static int resolve(svcb_model* m) {
     for (int k2 = i + 1; k2 < c.n_ups; ++k2) sf *= c.up_rates[k2];
     const int nk = (i + 1 == c.n_ups) ? 1 : 2 * sf;
     m->ups[i].noise = R.conv("dec.noise." + std::to_string(i), 1, ch / 2, nk);
+    if (nk > 8) {
+      ConvW& w = m->ups[i].noise_tc;
+      w.cin = sf; w.cout = ch / 2; w.k = 2; w.cout_pad = (w.cout + 7) / 8 * 8;
+      tc_tiling(w);
+      w.tc = reinterpret_cast<const uint8_t*>(
+          R.get("dec.noise." + std::to_string(i) + ".tc", (uint64_t)2 * 2 * w.cin_pad * w.ntiles * w.bn / 2));
+      w.b = m->ups[i].noise.b;
+    }
     ch /= 2;
   }
   m->res.resize((size_t)c.n_ups * c.n_res);

@@ -233,7 +233,7 @@ size_t conv_tc_smem_bytes(const ConvTcParams& p) {
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.Tout <= 0) return SVCB_OK;
   if ((p.kch != 32 && p.kch != 64) || p.cin_pad % p.kch || p.bn % 16 || p.bn < 16 || p.bn > 256 ||
-      p.ntiles * p.bn < p.Cout || (p.nsplit != 1 && p.nsplit != 3) || p.Tout != p.Tin) {
+      p.ntiles * p.bn < p.Cout || (p.nsplit != 1 && p.nsplit != 3) || p.Tout > p.Tin) {
     set_error("conv_tc: unsupported tiling (stride-1 'same' convolutions only)");
     return SVCB_E_BAD_SHAPE;
   }

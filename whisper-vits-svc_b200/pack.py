@@ -176,7 +176,15 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
             put(f"dec.ups.{i}.ph{r}.w", pack_conv(sub))
             put(f"dec.ups.{i}.ph{r}.tc", pack_conv_tc_general(sub))
         put(f"dec.ups.{i}.b", sd[f"dec.ups.{i}.bias"])
-        conv(f"dec.noise.{i}", sd[f"dec.noise_convs.{i}.weight"], sd[f"dec.noise_convs.{i}.bias"])
+        wn = sd[f"dec.noise_convs.{i}.weight"]
+        conv(f"dec.noise.{i}", wn, sd[f"dec.noise_convs.{i}.bias"])
+        if wn.shape[-1] > 8:
+            # long noise filter = Conv1d(1->C, K=2*sf, stride sf): on the source reshaped to sf "channels"
+            # per frame (space-to-depth) it is a 2-tap convolution, which the tensor-core conv handles:
+            # w2[co][ci][j] = w[co][0][sf*j + ci]
+            sf_ = wn.shape[-1] // 2
+            w2 = wn[:, 0, :].reshape(wn.shape[0], 2, sf_).permute(0, 2, 1).contiguous()
+            put(f"dec.noise.{i}.tc", pack_conv_tc_general(w2))
     n_blocks = cfg["n_ups"] * cfg["n_res"]
     for n in range(n_blocks):
         p = f"dec.resblocks.{n}"
