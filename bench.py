@@ -262,6 +262,10 @@ def run_ours(args, hp, sd):
         rep = lib.svcb_timing_report().decode()
         lib.svcb_timing_enable(0)
         import re
+        if os.environ.get("SVCB_DUMP_KERNELS"):
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            with open(os.path.join(ROOT, "gpurun_out", "kernels_raw.txt"), "w") as f:
+                f.write(rep)
         fam = {}
         for line in rep.strip().splitlines():
             nm, n, tms, fl, by = line.split()

@@ -23,7 +23,8 @@
 namespace svcb {
 
 constexpr int CT_M = 128;
-constexpr int CT_WST = 3;  // W ring depth
+constexpr int CT_WST = 3;  // W ring depth (max)
+static inline unsigned tc_cols(int n) { return n <= 32 ? 32u : n <= 64 ? 64u : n <= 128 ? 128u : n <= 256 ? 256u : 512u; }
 
 __device__ __forceinline__ float ct_act(float v, int act) {
   switch (act) {
@@ -39,8 +40,8 @@ __device__ __forceinline__ void ct_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(192, 1)
-conv_tc_kernel(const ConvTcParams p) {
+__global__ void __launch_bounds__(320, 1)
+conv_tc_kernel(const ConvTcParams p, const int wst) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[CT_WST], w_empty[CT_WST], bar_acc;
   __shared__ uint32_t tmem_slot;
@@ -62,7 +63,7 @@ conv_tc_kernel(const ConvTcParams p) {
 
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < CT_WST; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < wst; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     tc::mbar_init(&bar_acc, 1);
     tc::fence_barrier_init();
   }
@@ -115,18 +116,23 @@ conv_tc_kernel(const ConvTcParams p) {
       tc::fence_proxy_async_smem();
       ct_arrive(&a_full[buf]);
     }
-    // ---------------------------------------------------------------- epilogue
+  }
+  if (warp < 4 || warp >= 6) {
+    // ---------------------------------------------------------------- epilogue: two groups of four warps
+    // (the A producers, now idle, and warps 6-9) take alternate 16-column strips.  A warp may only
+    // read the TMEM lane quarter warp%4, so warps 6..9 own quarters 2,3,0,1.
+    const int grp = warp < 4 ? 0 : 1, wq = warp & 3;
     tc::mbar_wait(&bar_acc, 0);
     tc::fence_after_sync();
-    const int t = t0 + warp * 32 + lane;
+    const int t = t0 + wq * 32 + lane;
     const bool gate = (p.flags & CONV_GATE) != 0;
     const int cout_real = gate ? p.Cout / 2 : p.Cout;
     const bool keep = !(p.flags & CONV_OUT_MASK) || t < len;
     float* yb = p.y + (long long)b * cout_real * p.Tout;
     const float* rb = p.res ? p.res + (long long)b * cout_real * p.Tout : nullptr;
-    for (int c0 = 0; c0 < p.bn; c0 += 16) {
+    for (int c0 = grp * 16; c0 < p.bn; c0 += 32) {
       uint32_t v[16];
-      tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
       const bool live = t < p.Tout;
       const int step = gate ? 2 : 1;
       // residual / accumulator loads of the strip first (all in flight), stores afterwards
@@ -173,8 +179,8 @@ conv_tc_kernel(const ConvTcParams p) {
     // ---------------------------------------------------------------- W producer
     const int total = ncc * p.K * nparts;
     for (int i = 0; i < total; ++i) {
-      const int st = i % CT_WST;
-      if (i >= CT_WST) tc::mbar_wait(&w_empty[st], (uint32_t)(((i / CT_WST) - 1) & 1));
+      const int st = i % wst;
+      if (i >= wst) tc::mbar_wait(&w_empty[st], (uint32_t)(((i / wst) - 1) & 1));
       const int part = i % nparts, tap = (i / nparts) % p.K, cc = i / (nparts * p.K);
       const size_t tile = (((size_t)tap * ncc + cc) * 2 + part) * p.ntiles + nt;
       tc::mbar_arrive_expect_tx(&w_full[st], w_tile);
@@ -197,8 +203,8 @@ conv_tc_kernel(const ConvTcParams p) {
       for (int tap = 0; tap < p.K; ++tap) {
         const uint32_t row_off = (uint32_t)(tap * p.dil) * 16u;
         for (int part = 0; part < nparts; ++part, ++wi) {
-          const int st = wi % CT_WST;
-          tc::mbar_wait(&w_full[st], (uint32_t)((wi / CT_WST) & 1));
+          const int st = wi % wst;
+          tc::mbar_wait(&w_full[st], (uint32_t)((wi / wst) & 1));
           tc::fence_after_sync();
           const uint64_t bd0 = tc::smem_desc(w_base + (uint32_t)st * w_tile, lbo_b);
           const int n_a = (part == 0 && nparts == 2) ? 2 : 1;
@@ -224,10 +230,10 @@ conv_tc_kernel(const ConvTcParams p) {
   if (warp == 4) tc::tmem_dealloc(tmem, ncols);
 }
 
-size_t conv_tc_smem_bytes(const ConvTcParams& p) {
+static size_t conv_tc_smem_bytes(const ConvTcParams& p, int wst) {
   const int R = CT_M + (p.K - 1) * p.dil;
   const size_t a_buf = (size_t)(p.kch / 8) * R * 16 * (p.nsplit == 3 ? 2 : 1);
-  return 2 * a_buf + (size_t)CT_WST * p.kch * p.bn * 2 + 128;
+  return 2 * a_buf + (size_t)wst * p.kch * p.bn * 2 + 128;
 }
 
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
@@ -237,7 +243,11 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
     set_error("conv_tc: unsupported tiling (stride-1 'same' convolutions only)");
     return SVCB_E_BAD_SHAPE;
   }
-  const size_t smem = conv_tc_smem_bytes(p);
+  // a 2-deep weight ring when that lets two CTAs share an SM (one CTA's epilogue then overlaps the
+  // other's gather + MMA; the 1x1 convolutions are epilogue-bound), else the 3-deep ring
+  int wst = CT_WST;
+  if (conv_tc_smem_bytes(p, 2) <= 113 * 1024 && tc_cols(p.bn) <= 256) wst = 2;
+  const size_t smem = conv_tc_smem_bytes(p, wst);
   if (smem > 227 * 1024 - 512) { set_error("conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
@@ -252,7 +262,7 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
                  2.0 * p.Cin * p.K * p.Cout * (double)p.Tout * p.B,
                  4.0 * ((double)p.B * p.Cin * p.Tin + (double)p.B * cout_real * p.Tout * (p.res ? 2 : 1)) +
                      2.0 * (double)p.Cin * p.K * p.Cout);
-  conv_tc_kernel<<<grid, 192, smem, s>>>(p);
+  conv_tc_kernel<<<grid, 320, smem, s>>>(p, wst);
   SVCB_LAUNCH_CHECK("conv_tc");
   return SVCB_OK;
 }
