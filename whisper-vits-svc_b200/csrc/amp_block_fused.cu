@@ -40,80 +40,102 @@ struct AbCfg {
   static constexpr int THREADS = C <= 10 ? 512 : 384;
   static constexpr int NT = 2;                           // time steps per thread in the convolution
   static constexpr int W = NT * THREADS;                 // 1024 (C=10) / 768 (C=20)
+  static constexpr int ROWS8 = C <= 10 ? 8 : C;          // Snake rows done in 8-sample runs (rest: 4)
 };
 
 // SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
-// index inside the sequence.  Warp-private: a warp takes (channel, 64-output chunk) items, builds the
-// 2x-rate Snake values of its chunk in its own scratch slice and decimates them — only __syncwarp,
-// no CTA barrier inside the activation.
-constexpr int AB_CH = 58;   // outputs per item: 58 + 6 = 64 up-sampling positions = two full warp passes
-constexpr int AB_VSL = 2 * (AB_CH + 6) + 4;  // scratch floats per warp (slot 0 unused: tap 0 lands on an even index)
+// index inside the sequence.  Register-resident: a thread owns R consecutive outputs of one channel,
+// loads the R+16 inputs around them with 16-byte shared loads, forms the 2(R+6) up-sampled Snake
+// values in registers and decimates them — no scratch buffer, no barrier, and R+6 independent
+// dependency chains per thread (the earlier warp-private version ran one 12-deep FMA chain per
+// thread on 12 resident warps and was latency-bound: profiles/r01_notes.md §7).
+//   position a = n0-3+p (p in [0,R+6)):  u[2a]   = 2*sum_{d=0..5} x[a-3+d] f[11-2d]
+//                                        u[2a+1] = 2*sum_{d=1..6} x[a-3+d] f[12-2d]
+//   v = u + sin^2(u e^alpha) / (e^beta + 1e-9);   out[n] = sum_{k<12} v[2n-5+k] f[k]
+// (alias/resample.py:25-33, alias/act.py:79-92, alias/filter.py:86-94).  Runs that touch the
+// sequence ends take a scalar path with the replicate-padding clamps.
+template <int R>
+__device__ __forceinline__ void ab_snake_run(const float* __restrict__ xr, float* __restrict__ dr, int n0,
+                                             const float (&fu)[12], const float (&fdn)[12],
+                                             const float* f_up, const float* f_dn, float a_, float b_,
+                                             int lo_i, int hi_i, bool seq_lo, bool seq_hi) {
+  // the clamped path is only needed where a tap crosses a real sequence end; at a mere tile edge the
+  // guard band is read instead — those outputs lie in the halo and are never used
+  if (!((seq_lo && n0 - 6 < lo_i) || (seq_hi && n0 + R + 5 > hi_i))) {
+    float x[R + 16];  // xr[n0-8 .. n0+R+8)
+#pragma unroll
+    for (int q = 0; q < (R + 16) / 4; ++q) {
+      const float4 t4 = *reinterpret_cast<const float4*>(xr + n0 - 8 + 4 * q);
+      x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+    }
+    float vv[2 * R + 12];
+#pragma unroll
+    for (int p = 0; p < R + 6; ++p) {
+      float ue = x[p + 2] * fu[11];
+      ue = fmaf(x[p + 3], fu[9], ue); ue = fmaf(x[p + 4], fu[7], ue); ue = fmaf(x[p + 5], fu[5], ue);
+      ue = fmaf(x[p + 6], fu[3], ue); ue = fmaf(x[p + 7], fu[1], ue);
+      float uo = x[p + 3] * fu[10];
+      uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
+      uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
+      ue *= 2.f; uo *= 2.f;
+      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
+      vv[2 * p] = fmaf(b_, se * se, ue);
+      vv[2 * p + 1] = fmaf(b_, so * so, uo);
+    }
+    float o[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fmaf(vv[2 * i + 1 + k], fdn[k], acc);
+      o[i] = acc;
+    }
+#pragma unroll
+    for (int q = 0; q < R / 4; ++q)
+      *reinterpret_cast<float4*>(dr + n0 + 4 * q) = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  } else {
+    const int mlo = 2 * lo_i, mhi = 2 * hi_i + 1;
+    for (int i = 0; i < R; ++i) {
+      const int n = n0 + i;
+      float acc = 0.f;
+      if (n >= lo_i && n <= hi_i) {
+        for (int k = 0; k < 12; ++k) {
+          const int m = min(max(2 * n - 5 + k, mlo), mhi);
+          const int a = m >> 1, q = m & 1;
+          float u = 0.f;
+          for (int d = q; d < q + 6; ++d) u = fmaf(xr[min(max(a - 3 + d, lo_i), hi_i)], f_up[11 + q - 2 * d], u);
+          u *= 2.f;
+          const float sn = __sinf(u * a_);
+          acc = fmaf(fmaf(b_, sn * sn, u), f_dn[k], acc);
+        }
+      }
+      dr[n] = acc;  // zero outside the sequence = zero padding of the next conv
+    }
+  }
+}
 
+// Rows [0, ROWS8) are covered by 8-sample runs and the remaining rows by 4-sample runs, chosen so
+// that both task counts are whole multiples of the CTA size (C=20: 20 rows x 96 runs = 5 x 384;
+// C=10: 8 x 128 = 2 x 512 and 2 x 256 = 512) — no partially filled pass.
 template <int C>
-__device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst, float* V,
+__device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst,
                                          const float* f_up, const float* f_dn, const float* ea,
-                                         const float* ib, int W, int WS, int lo_i, int hi_i, int tid) {
+                                         const float* ib, int lo_i, int hi_i, bool seq_lo, bool seq_hi, int tid) {
   constexpr int AB_THREADS = AbCfg<C>::THREADS;
-  const int warp = tid >> 5, lane = tid & 31;
-  float* vw = V + warp * AB_VSL;
-  const int nchunks = (W + AB_CH - 1) / AB_CH;
-  const int mlo = 2 * lo_i, mhi = 2 * hi_i + 1;
+  constexpr int W = AbCfg<C>::W, WS = W + 2 * AB_GUARD;
+  constexpr int ROWS8 = AbCfg<C>::ROWS8;
+  constexpr int T8 = ROWS8 * (W / 8), T4 = (C - ROWS8) * (W / 4);
+  static_assert(T8 % AB_THREADS == 0 && T4 % AB_THREADS == 0, "Snake passes must be exactly filled");
   float fu[12], fdn[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) { fu[k] = f_up[k]; fdn[k] = f_dn[k]; }
-  for (int item = warp; item < C * nchunks; item += AB_THREADS / 32) {
-    const int c = item / nchunks, n0 = (item - c * nchunks) * AB_CH;
-    const float* xr = src + c * WS + AB_GUARD;
-    const float a_ = ea[c], b_ = ib[c];
-    // chunk-uniform: does any tap of this chunk leave the sequence (replicate padding needed)?
-    const bool interior = (n0 - 6 >= lo_i) && (n0 + AB_CH + 5 <= hi_i);
-#pragma unroll
-    for (int pass = 0; pass < (AB_CH + 6) / 32; ++pass) {
-      const int ai = lane + 32 * pass;
-      const int a = n0 - 3 + ai;
-      float x[7];
-      if (interior) {
-#pragma unroll
-        for (int d = 0; d < 7; ++d) x[d] = xr[a - 3 + d];
-      } else {
-#pragma unroll
-        for (int d = 0; d < 7; ++d) x[d] = xr[min(max(a - 3 + d, lo_i), hi_i)];
-      }
-      float ue = x[0] * fu[11];
-      ue = fmaf(x[1], fu[9], ue); ue = fmaf(x[2], fu[7], ue); ue = fmaf(x[3], fu[5], ue);
-      ue = fmaf(x[4], fu[3], ue); ue = fmaf(x[5], fu[1], ue);
-      float uo = x[1] * fu[10];
-      uo = fmaf(x[2], fu[8], uo); uo = fmaf(x[3], fu[6], uo); uo = fmaf(x[4], fu[4], uo);
-      uo = fmaf(x[5], fu[2], uo); uo = fmaf(x[6], fu[0], uo);
-      ue *= 2.f; uo *= 2.f;
-      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
-      vw[2 * ai + 1] = fmaf(b_, se * se, ue);    // v[2a]   at j = m - 2*(n0-3) + 1
-      vw[2 * ai + 2] = fmaf(b_, so * so, uo);    // v[2a+1]
-    }
-    __syncwarp();
-    const int jbase = 2 * (n0 - 3) - 1;
-    for (int ni = lane; ni < AB_CH; ni += 32) {
-      const int n = n0 + ni;
-      if (n >= W) break;
-      float o = 0.f;
-      if (n >= lo_i && n <= hi_i) {
-        const int m0 = 2 * n - 5;
-        if (m0 >= mlo && m0 + 11 <= mhi) {
-          const float2* vp = reinterpret_cast<const float2*>(vw + (m0 - jbase));  // even index
-#pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            const float2 v2 = vp[k];
-            o = fmaf(v2.x, fdn[2 * k], o);
-            o = fmaf(v2.y, fdn[2 * k + 1], o);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 12; ++k) o = fmaf(vw[min(max(m0 + k, mlo), mhi) - jbase], fdn[k], o);
-        }
-      }
-      dst[c * WS + AB_GUARD + n] = o;  // zero outside the sequence = zero padding of the next conv
-    }
-    __syncwarp();
+  for (int task = tid; task < T8; task += AB_THREADS) {
+    const int c = task / (W / 8), n0 = (task - c * (W / 8)) * 8;
+    ab_snake_run<8>(src + c * WS + AB_GUARD, dst + c * WS + AB_GUARD, n0, fu, fdn, f_up, f_dn, ea[c], ib[c], lo_i, hi_i, seq_lo, seq_hi);
+  }
+  for (int task = tid; task < T4; task += AB_THREADS) {
+    const int c = ROWS8 + task / (W / 4), n0 = (task % (W / 4)) * 4;
+    ab_snake_run<4>(src + c * WS + AB_GUARD, dst + c * WS + AB_GUARD, n0, fu, fdn, f_up, f_dn, ea[c], ib[c], lo_i, hi_i, seq_lo, seq_hi);
   }
 }
 
@@ -194,10 +216,10 @@ amp_block_fused_kernel(const AmpBlockParams p) {
   float* X = ab_smem;
   float* Y = X + C * WS;
   float* Z = Y + C * WS;
-  float* V = Z + C * WS;                       // per-warp Snake scratch
-  float* wsm = V + (AB_THREADS / 32) * AB_VSL; // [C][K][CP]
+  float* wsm = Z + C * WS;                     // [C][K][CP]
   const int base = t0 - H;                     // sequence position of buffer index 0
   const int lo_i = max(0, -base), hi_i = min(W - 1, p.L - 1 - base);
+  const bool seq_lo = base <= 0, seq_hi = base + W >= p.L;  // does the buffer contain a sequence end?
 
   // zero everything once (guard bands must stay zero), then load x
   for (int i = tid; i < 3 * C * WS; i += AB_THREADS) X[i] = 0.f;
@@ -224,15 +246,10 @@ amp_block_fused_kernel(const AmpBlockParams p) {
         wsm[i] = co < p.cout_pad ? __ldg(wg + (long long)cj * p.cout_pad + co) : 0.f;
       }
       __syncthreads();
-      if (half == 0) {
-        ab_snake<C>(X, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
-        __syncthreads();
-        ab_conv<C, K, false>(Y, Z, wsm, s_bias, p.dil[d], W, WS, lo_i, hi_i, tid);
-      } else {
-        ab_snake<C>(Z, Y, V, f_up, f_dn, s_ea, s_ib, W, WS, lo_i, hi_i, tid);
-        __syncthreads();
-        ab_conv<C, K, true>(Y, X, wsm, s_bias, 1, W, WS, lo_i, hi_i, tid);
-      }
+      ab_snake<C>(half == 0 ? X : Z, Y, f_up, f_dn, s_ea, s_ib, lo_i, hi_i, seq_lo, seq_hi, tid);
+      __syncthreads();
+      if (half == 0) ab_conv<C, K, false>(Y, Z, wsm, s_bias, p.dil[d], W, WS, lo_i, hi_i, tid);
+      else ab_conv<C, K, true>(Y, X, wsm, s_bias, 1, W, WS, lo_i, hi_i, tid);
       __syncthreads();
     }
   }
@@ -257,7 +274,7 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   const int H = ab_halo(p.K, p.dil);
   const int W = AbCfg<C>::W, WS = W + 2 * AB_GUARD, TOUT = W - 2 * H;
   if (TOUT < 64) { set_error("amp_block_fused: receptive field too large for the tile"); return SVCB_E_UNSUPPORTED; }
-  const size_t smem = ((size_t)3 * C * WS + (AB_THREADS / 32) * AB_VSL + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
+  const size_t smem = ((size_t)3 * C * WS + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
   if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
