@@ -262,7 +262,7 @@ amp_block_fused_kernel(const AmpBlockParams p) {
       float o = X[c * WS + AB_GUARD + H + n];
       const long long off = (long long)c * p.L + t;
       if (p.accum) o += yb[off];
-      if (p.out_div != 0.f) o = o / p.out_div;
+      if (p.out_div != 0.f) { asm volatile(""); o = o / p.out_div; }  // keep a uniform branch (no if-converted x/0)
       yb[off] = o;
     }
   }

@@ -319,6 +319,7 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
     // DRAM-latency pipeline: measured 1.4 us per strip when each strip waited for its own loads).
     const int grp = warp >> 2, wq = warp & 3;
     const int nstrips = p.Cp / 16;
+    const bool do_div = p.out_div != 0.f;
     int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
@@ -355,7 +356,9 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
             const int co = strip * 16 + j;
             if (co < p.C) {
               float o = __uint_as_float(v[j]) + __ldg(p.bias + co) + cur[j];
-              if (p.out_div != 0.f) o = o / p.out_div;
+              // a real (uniform) branch: if-converted, the division ran its x/0 slow path per element
+              // on every launch without a divisor (r01 source-level capture: 30 % of all instructions)
+              if (do_div) { asm volatile(""); o = o / p.out_div; }
               p.y[rowb + (long long)co * p.L] = o;
             }
           }

@@ -129,7 +129,7 @@ conv1d_kernel(const ConvParams p, const int ci_tile, const int xspan) {
       if (rb) v += rb[off];
       if (p.addvec) v += __ldg(p.addvec + to * cout_real + co);
       if (p.flags & CONV_ACCUM) v += yb[off];
-      if (p.out_div != 0.f) v = v / p.out_div;
+      if (p.out_div != 0.f) { asm volatile(""); v = v / p.out_div; }
       yb[off] = v;
     };
     if (p.flags & CONV_GATE) {
