@@ -164,6 +164,15 @@ size_t svcb_whisper_workspace_bytes(const svcb_whisper* w, int32_t B, int32_t n_
 int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int32_t B, int32_t n_frames,
                         void* ws, size_t ws_bytes, svcb_stream stream);
 
+/* Replaces whisper.audio.log_mel_spectrogram (whisper/audio.py:68-100) plus the extractor's mel noise
+ * (whisper/inference.py:46,58) for B equal-length chunks of 16 kHz audio already on the device:
+ * audio [B, n_samples] fp32 -> mel [B, n_mels, n_samples/160] fp32 (Hann STFT 400/160, reflect-centred,
+ * last frame dropped, |.|^2, mel_filters [n_mels, 201] fp32, log10 clamp 1e-10, per-chunk max-8 floor,
+ * (x+4)/4, + noise_gain * noise when noise != NULL).  scratch: >= 4*B bytes of device memory. */
+int svcb_whisper_log_mel(const float* audio, const float* mel_filters, const float* noise, float noise_gain,
+                         float* mel, void* scratch, int32_t B, int32_t n_samples, int32_t n_mels,
+                         svcb_stream stream);
+
 /* Operator entry points of the encoder (unit tests):
  * out[M,N] = A[M,K] . W[N,K]^T + bias with epilogue 0: bf16 row-major out, 1: GELU(erf) then bf16
  * out as the GEMM tile image ([ceil(M/128)][N/64][8][128][8], the A operand of a following GEMM),

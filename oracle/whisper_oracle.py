@@ -65,3 +65,49 @@ def audio_encoder(ckpt: dict, mel: torch.Tensor, stages: dict | None = None) -> 
             if stages is not None:
                 stages[f"block{i}"] = x
         return F.layer_norm(x, (D,), sd["encoder.ln_post.weight"], sd["encoder.ln_post.bias"])
+
+
+# ------------------------------------------------------------------ log-mel front end (whisper/audio.py)
+SAMPLE_RATE, N_FFT, HOP_LENGTH, N_MELS = 16000, 400, 160, 80
+
+
+def slaney_mel_filterbank(n_mels: int = N_MELS, sr: int = SAMPLE_RATE, n_fft: int = N_FFT) -> np.ndarray:
+    """The matrix whisper/audio.py:54-65 obtains from `librosa.filters.mel(sr=16000, n_fft=400, n_mels=80)`
+    (librosa defaults: Slaney mel scale — linear below 1 kHz at 200/3 Hz per mel, logarithmic above with
+    27 steps per factor 6.4 — triangular filters between consecutive mel-spaced corner frequencies,
+    each scaled by 2 / (f_hi - f_lo)).  librosa is a requirements.txt dependency that is absent from
+    this image and the reference ships no copy of the matrix: the filterbank is restated from the
+    published definition and pinned against an independent third-party implementation that IS in the
+    image — transformers 5.5 `audio_utils.mel_filter_bank(norm="slaney", mel_scale="slaney")` and
+    `WhisperFeatureExtractor._np_extract_fbank_features` (tests/test_oracle_cpu.py: 1e-9 / 1e-6)."""
+    def hz_to_mel(f):
+        return f / (200.0 / 3) if f < 1000.0 else 15.0 + math.log(f / 1000.0) / (math.log(6.4) / 27.0)
+
+    def mel_to_hz(m):
+        return (200.0 / 3) * m if m < 15.0 else 1000.0 * math.exp((math.log(6.4) / 27.0) * (m - 15.0))
+
+    top = hz_to_mel(sr / 2.0)
+    corners = [mel_to_hz(top * i / (n_mels + 1)) for i in range(n_mels + 2)]
+    nb = n_fft // 2 + 1
+    fb = np.zeros((n_mels, nb), dtype=np.float64)
+    for m in range(n_mels):
+        lo, mid, hi = corners[m], corners[m + 1], corners[m + 2]
+        for k in range(nb):
+            f = k * sr / n_fft
+            tri = min((f - lo) / (mid - lo), (hi - f) / (hi - mid))
+            if tri > 0.0:
+                fb[m, k] = tri * 2.0 / (hi - lo)
+    return fb.astype(np.float32)
+
+
+def log_mel_spectrogram(audio: torch.Tensor, n_mels: int = N_MELS) -> torch.Tensor:
+    """whisper/audio.py:68-100: Hann STFT (400 / 160, torch.stft defaults = centred, reflect padding),
+    squared magnitude without the last frame, mel projection, log10 of the 1e-10 clamp, `max - 8`
+    floor over the whole chunk, (x + 4) / 4.  audio [n_samples] -> [n_mels, n_samples // 160]."""
+    window = torch.hann_window(N_FFT)
+    stft = torch.stft(audio.float(), N_FFT, HOP_LENGTH, window=window, return_complex=True)
+    magnitudes = stft[..., :-1].abs() ** 2
+    mel_spec = torch.from_numpy(slaney_mel_filterbank(n_mels)) @ magnitudes
+    log_spec = torch.clamp(mel_spec, min=1e-10).log10()
+    log_spec = torch.maximum(log_spec, log_spec.max() - 8.0)
+    return (log_spec + 4.0) / 4.0

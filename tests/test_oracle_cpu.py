@@ -80,3 +80,41 @@ def test_f0_to_coarse_integer_hz_is_rounding_safe():
     mel = mel.clamp(min=1.0, max=255.0)
     assert torch.equal((mel + 0.5).long(), ref)
     assert ref.min() >= 1 and ref.max() <= 255
+
+
+# ------------------------------------------------------------------ log-mel front end (whisper/audio.py:54-100)
+def test_mel_filterbank_pinned_by_third_party():
+    """librosa (the reference's source of the matrix, whisper/audio.py:54-65) is absent: pin the
+    restated Slaney filterbank on transformers' independent implementation of the same definition."""
+    au = pytest.importorskip("transformers.audio_utils")
+    from oracle import whisper_oracle as wo
+    fb = au.mel_filter_bank(num_frequency_bins=201, num_mel_filters=80, min_frequency=0.0, max_frequency=8000.0,
+                            sampling_rate=16000, norm="slaney", mel_scale="slaney")
+    ours = wo.slaney_mel_filterbank()
+    assert ours.shape == (80, 201)
+    assert np.abs(ours - fb.T).max() < 1e-8
+    # structure: non-negative triangles, one peak each, area ~ 1 under the Slaney normalisation
+    assert (ours >= 0).all()
+    assert np.all(np.diff(ours.argmax(axis=1)) >= 0)
+    assert np.allclose(ours.sum(axis=1) * (16000 / 400), 1.0, atol=0.1)   # 40 Hz bins sample narrow triangles coarsely
+
+
+def test_log_mel_oracle_pinned_by_third_party():
+    tr = pytest.importorskip("transformers")
+    from oracle import whisper_oracle as wo
+    fe = tr.WhisperFeatureExtractor(feature_size=80)
+    rs = np.random.RandomState(3)
+    t = np.arange(16000 * 4) / 16000.0
+    for x in (rs.randn(16000 * 4).astype(np.float32) * 0.1,
+              (0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.01 * rs.randn(t.size)).astype(np.float32),
+              np.zeros(16000 * 2 + 37, np.float32)):
+        ref = fe._np_extract_fbank_features(x[None, :], "cpu")[0]
+        got = wo.log_mel_spectrogram(torch.from_numpy(x)).numpy()
+        assert got.shape == ref.shape == (80, x.size // 160)
+        assert np.abs(got - ref).max() < 2e-4   # near-floor bins of the tone: fp32 FFT vs numpy float64
+
+
+def test_product_mel_filters_match_oracle():
+    from oracle import whisper_oracle as wo
+    from whisper_vits_svc_b200 import whisper_infer
+    assert np.array_equal(whisper_infer.mel_filters().numpy(), wo.slaney_mel_filterbank())

@@ -4,6 +4,8 @@ runs fp16 on GPU (whisper/inference.py:22-23), so the gate is relative: rel-L2 <
 cosine >= 0.999 against the fp32 oracle (SURVEY.md §8c tolerance plan)."""
 import ctypes
 
+import numpy as np
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -89,3 +91,69 @@ def test_encoder_vs_oracle(state, heads, layers, B, n):
     cos = float(F.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
     print(f"whisper D={state} layers={W.kept_layers(dims)}: rel-l2 {r:.3e}, cosine {cos:.6f}, max-abs {max_abs(got, ref):.3e}")
     assert r <= 2e-2 and cos >= 0.999
+
+
+def _small_encoder():
+    from whisper_vits_svc_b200 import whisper_infer
+    dims = dict(synth.WHISPER_LARGE_V2_DIMS, n_audio_state=256, n_audio_head=4, n_audio_layer=4)
+    ck = synth.whisper_checkpoint(dims, seed=11)
+    return ck, whisper_infer.WhisperB200(ck, "cuda")
+
+
+@pytest.mark.parametrize("B,N", [(1, 16000 * 3), (3, 16000 * 15), (2, 16000 * 2 + 37), (1, 201), (2, 480000)])
+def test_log_mel_device_vs_oracle(B, N):
+    """svcb_whisper_log_mel vs the torch restatement of whisper/audio.py:68-100 (itself pinned on the
+    transformers implementation in the CPU suite).  White noise, a tone over a noise floor, silence."""
+    _, wm = _small_encoder()
+    rs = np.random.RandomState(N % 9973)
+    t = np.arange(N) / 16000.0
+    items = []
+    for b in range(B):
+        if b % 3 == 0:
+            items.append(rs.randn(N).astype(np.float32) * 0.1)
+        elif b % 3 == 1:
+            items.append((0.3 * np.sin(2 * np.pi * (220.0 * (b + 1)) * t) + 0.01 * rs.randn(N)).astype(np.float32))
+        else:
+            items.append(np.zeros(N, np.float32))
+    audio = torch.from_numpy(np.stack(items))
+    ref = torch.stack([W.log_mel_spectrogram(a) for a in audio])
+    got = wm.encoder.log_mel(audio).cpu()
+    assert got.shape == ref.shape == (B, 80, N // 160)
+    d = (got - ref).abs()
+    print(f"log-mel B={B} N={N}: max-abs {float(d.max()):.3e}, mean-abs {float(d.mean()):.3e}")
+    # direct fp32 DFT vs torch's FFT: bins near the max-8 floor of a tonal frame differ most
+    assert float(d.max()) <= 5e-3 and float(d.mean()) <= 1e-4
+    # the extractor's noise term is fused into the same pass (whisper/inference.py:46,58)
+    nz = torch.randn(B, 80, N // 160, generator=torch.Generator().manual_seed(5))
+    got_n = wm.encoder.log_mel(audio, nz, 0.1).cpu()
+    assert max_abs(got_n, got + 0.1 * nz) <= 1e-6
+
+
+def test_pred_ppg_end_to_end_vs_oracle(tmp_path):
+    """pred_ppg (whisper/inference.py:32-62): wav file -> 15 s chunks + remainder -> device log-mel
+    (+ the given noise) -> encoder -> row trim -> .npy, against the oracle on the same noise."""
+    from scipy.io import wavfile
+    from whisper_vits_svc_b200 import whisper_infer
+    ck, wm = _small_encoder()
+    rs = np.random.RandomState(2)
+    n = 16000 * 33 + 1234                       # two full chunks + a remainder
+    wav = (rs.randn(n) * 0.05).astype(np.float32)
+    path = str(tmp_path / "a.wav")
+    wavfile.write(path, 16000, (wav * 32767).astype(np.int16))
+    audio = whisper_infer.load_audio(path)
+    plan = whisper_infer.chunk_plan(audio.shape[0])
+    assert [e - s for s, e, _ in plan] == [240000, 240000, n - 480000]
+    g = torch.Generator().manual_seed(8)
+    noise = [torch.randn(80, (e - s) // 160, generator=g) for s, e, _ in plan]
+    out = str(tmp_path / "a.ppg.npy")
+    whisper_infer.pred_ppg(wm, path, out, "cuda", mel_noise=noise)
+    got = np.load(out)
+    rows = []
+    for (s, e, n_rows), nz in zip(plan, noise):
+        mel = W.log_mel_spectrogram(torch.from_numpy(audio[s:e])) + nz * 0.1
+        rows.append(W.audio_encoder(ck, mel.unsqueeze(0))[0][:n_rows])
+    ref = torch.cat(rows).numpy()
+    assert got.shape == ref.shape and got.shape[0] == 750 + 750 + (audio.shape[0] - 480000) // 320
+    r = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+    print(f"pred_ppg: rows {got.shape[0]}, rel-l2 {r:.3e}")
+    assert r <= 2e-2

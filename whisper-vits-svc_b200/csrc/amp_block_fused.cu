@@ -77,8 +77,7 @@ __device__ __forceinline__ void ab_snake_run(const float* __restrict__ xr, float
       float uo = x[p + 3] * fu[10];
       uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
       uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
-      ue *= 2.f; uo *= 2.f;
-      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
+      const float se = __sinf(ue * a_), so = __sinf(uo * a_);   // (the x2 gain is folded into fu: exact)
       vv[2 * p] = fmaf(b_, se * se, ue);
       vv[2 * p + 1] = fmaf(b_, so * so, uo);
     }
@@ -128,7 +127,7 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
   static_assert(T8 % AB_THREADS == 0 && T4 % AB_THREADS == 0, "Snake passes must be exactly filled");
   float fu[12], fdn[12];
 #pragma unroll
-  for (int k = 0; k < 12; ++k) { fu[k] = f_up[k]; fdn[k] = f_dn[k]; }
+  for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }  // UpSample1d's ratio gain (resample.py:31)
   for (int task = tid; task < T8; task += AB_THREADS) {
     const int c = task / (W / 8), n0 = (task - c * (W / 8)) * 8;
     ab_snake_run<8>(src + c * WS + AB_GUARD, dst + c * WS + AB_GUARD, n0, fu, fdn, f_up, f_dn, ea[c], ib[c], lo_i, hi_i, seq_lo, seq_hi);

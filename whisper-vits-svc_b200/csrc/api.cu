@@ -473,7 +473,17 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     fp.src = fuse_noise ? source : nullptr; fp.wn = us.noise.w; fp.bn = us.noise.b; fp.Kn = Kn;
     fp.sf = last ? 1 : sf; fp.padn = last ? 0 : sf / 2; fp.cout_pad = us.noise.cout_pad; fp.Ltot = Ltot;
     size_t slab = 0;
-    for (int r = 0; r < us.rate; ++r) {
+    const bool fused_up = c.precision != 0 && fuse_noise && ups_fused_supported(ch, chn, us.rate, us.taps, Kn);
+    if (fused_up) {  // narrow stages: transposed conv + noise conv + biases in one fp32 pass
+      UpsFusedParams q;
+      q.x = x; q.wph[0] = us.phase[0].w; q.wph[1] = us.phase[1].w; q.bias = us.bias;
+      q.src = source; q.wn = us.noise.w; q.bn = us.noise.b; q.y = X;
+      q.B = B; q.Cin = ch; q.Cout = chn; q.L = L; q.Ln = Ln; q.rate = us.rate; q.M = us.taps; q.pad = us.pad;
+      q.cout_pad = us.phase[0].cout_pad; q.Kn = Kn; q.sf = fp.sf; q.padn = fp.padn;
+      q.cout_pad_n = us.noise.cout_pad; q.Ltot = Ltot;
+      RUN(launch_ups_fused(q, s));
+    }
+    for (int r = 0; r < us.rate && !fused_up; ++r) {
       ConvParams p = std_conv(us.phase[r], x, nullptr, B, L, Ln, us.taps - 1);
       p.bias = nullptr;
       const int pr = us.pad - r;
@@ -499,7 +509,7 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
         RUN(launch_conv1d(p, s));
       }
     }
-    if (!ctx.dry) SVCB_TRY(launch_ups_finalize(fp, B, s));
+    if (!ctx.dry && !fused_up) SVCB_TRY(launch_ups_finalize(fp, B, s));
     if (!fuse_noise && c.precision != 0 && us.noise_tc.tc && sf <= 2 * SRC_PADF && !last) {
       // long noise filter as Conv1d(sf -> C, K=2) over the space-to-depth view of the padded source:
       // x[b, ci, t] = srcp[b][32 - sf/2 + sf*t + ci]

@@ -111,6 +111,24 @@ struct AmpBlockParams {
   float out_div = 0.f;           // then / out_div when != 0
 };
 int launch_amp_block_fused(const AmpBlockParams& p, cudaStream_t s);
+
+// polyphase ConvTranspose1d (rate 2, 2 taps per phase) + short noise conv + biases in one pass
+struct UpsFusedParams {
+  const float* x = nullptr;            // [B][Cin][L]
+  const float* wph[2] = {nullptr, nullptr};  // phase sub-filters, packed [Cin][M][cout_pad]
+  const float* bias = nullptr;         // [Cout]
+  const float* src = nullptr;          // harmonic source [B][Ltot]
+  const float* wn = nullptr;           // noise conv, packed [1][Kn][cout_pad_n]
+  const float* bn = nullptr;           // [Cout]
+  float* y = nullptr;                  // [B][Cout][Ln]
+  int B = 0, Cin = 0, Cout = 0, L = 0, Ln = 0, rate = 0, M = 0, pad = 0, cout_pad = 0;
+  int Kn = 0, sf = 1, padn = 0, cout_pad_n = 0;
+  long long Ltot = 0;
+};
+int launch_ups_fused(const UpsFusedParams& p, cudaStream_t s);
+int launch_log_mel(const float* audio, const float* filt, const float* noise, float gain, float* out,
+                   unsigned* scratch, int B, int N, int n_mels, cudaStream_t s);
+bool ups_fused_supported(int Cin, int Cout, int rate, int taps, int Kn);
 bool amp_block_fused_supported(int C, int K, const int* dil);
 
 // ----------------------------------------------------------------------------- general tensor-core conv

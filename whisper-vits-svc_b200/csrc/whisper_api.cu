@@ -164,6 +164,15 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
 }
 
 
+int svcb_whisper_log_mel(const float* audio, const float* mel_filters, const float* noise, float noise_gain,
+                         float* mel, void* scratch, int32_t B, int32_t n_samples, int32_t n_mels,
+                         svcb_stream stream) {
+  if (!audio || !mel_filters || !mel || !scratch) { set_error("log_mel: null pointer"); return SVCB_E_BAD_SHAPE; }
+  if (B < 0 || n_samples < 0 || n_mels <= 0) { set_error("log_mel: bad shape"); return SVCB_E_BAD_SHAPE; }
+  return launch_log_mel(audio, mel_filters, noise, noise_gain, mel, static_cast<unsigned*>(scratch), B, n_samples,
+                        n_mels, static_cast<cudaStream_t>(stream));
+}
+
 size_t svcb_op_gemm_bf16_scratch_bytes(int32_t M, int32_t N, int32_t K) {
   return ((size_t)(M + 127) / 128 * 128 * K + (size_t)N * K) * 2 + 1024;
 }

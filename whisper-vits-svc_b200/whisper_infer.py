@@ -9,9 +9,11 @@ operands with fp32 accumulation and an fp32 residual stream.
 
 `pred_ppg(whisper, wavPath, ppgPath, device)` keeps the reference's framing (15 s chunks + remainder,
 0.1*randn mel noise, row trim to samples//320, np.save; whisper/inference.py:32-62) but runs all
-chunks of a file as ONE batch.  The log-mel front-end (whisper/audio.py:54-100) is host-side torch
-here, as it is in the reference (SURVEY.md §8f-1 lists the on-device version as the next row); the
-Slaney mel filterbank is restated because librosa is not a dependency.
+chunks of a file as ONE batch.  The log-mel front-end (whisper/audio.py:54-100) runs on the device
+too (`svcb_whisper_log_mel`): the audio is uploaded once, STFT / mel / log / noise
+happen in three launches and the mel tensor never visits the host.  The Slaney mel filterbank is
+restated here (host, once) because librosa is not a dependency; the torch restatement of the whole
+front end lives in oracle/whisper_oracle.py and is what the GPU test compares against.
 """
 from __future__ import annotations
 
@@ -106,6 +108,8 @@ class WhisperEncoderB200:
         blob_cpu, table = pack.build_blob(items)
         self._install(blob_cpu.to(self.device), table)
         self._ws = None
+        self._filters = mel_filters(self.cfg["n_mels"]).to(self.device).contiguous()
+        self._lm_scratch = None
 
     def _install(self, blob, table):
         lib = _lib.load()
@@ -144,6 +148,31 @@ class WhisperEncoderB200:
                                          self._ws.numel(), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(st, "svcb_whisper_encode")
         return out
+
+
+    @torch.no_grad()
+    def log_mel(self, audio: torch.Tensor, noise: Optional[torch.Tensor] = None, noise_gain: float = 0.1) -> torch.Tensor:
+        """whisper/audio.py:68-100 (+ the extractor's `mel + randn_like(mel) * 0.1`, whisper/inference.py:46,58)
+        on the device: audio [B, n_samples] (16 kHz) -> mel [B, n_mels, n_samples // 160] fp32."""
+        audio = audio.to(self.device, torch.float32).contiguous()
+        if audio.dim() == 1:
+            audio = audio.unsqueeze(0)
+        B, N = audio.shape
+        nm = self.cfg["n_mels"]
+        F = N // HOP_LENGTH
+        mel = torch.empty(B, nm, F, device=self.device, dtype=torch.float32)
+        if noise is not None:
+            noise = noise.to(self.device, torch.float32).contiguous()
+            assert tuple(noise.shape) == (B, nm, F)
+        if self._lm_scratch is None or self._lm_scratch.numel() < B:
+            self._lm_scratch = torch.empty(max(B, 64), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            st = _lib.load().svcb_whisper_log_mel(
+                audio.data_ptr(), self._filters.data_ptr(), noise.data_ptr() if noise is not None else None,
+                float(noise_gain), mel.data_ptr(), self._lm_scratch.data_ptr(), B, N, nm,
+                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "svcb_whisper_log_mel")
+        return mel
 
 
 class WhisperB200:
@@ -192,18 +221,6 @@ def mel_filters(n_mels: int = N_MELS, sr: int = SAMPLE_RATE, n_fft: int = N_FFT)
     return torch.from_numpy((w * enorm[:, None]).astype(np.float32))
 
 
-def log_mel_spectrogram(audio: torch.Tensor, n_mels: int = N_MELS) -> torch.Tensor:
-    """whisper/audio.py:68-100: Hann STFT(400,160), |.|^2 without the last frame, mel, log10 clamp,
-    max-8 floor, (x+4)/4."""
-    window = torch.hann_window(N_FFT).to(audio.device)
-    stft = torch.stft(audio, N_FFT, HOP_LENGTH, window=window, return_complex=True)
-    mag = stft[..., :-1].abs() ** 2
-    mel = mel_filters(n_mels).to(audio.device) @ mag
-    log = torch.clamp(mel, min=1e-10).log10()
-    log = torch.maximum(log, log.max() - 8.0)
-    return (log + 4.0) / 4.0
-
-
 def load_audio(path: str, sr: int = SAMPLE_RATE) -> np.ndarray:
     """whisper/audio.py:24-26 uses librosa.load(sr=16000) (mono float32, resampled); restated with
     scipy: int PCM -> [-1,1), channel mean, polyphase resampling."""
@@ -236,22 +253,24 @@ def chunk_plan(audln: int, chunk: int = 15 * SAMPLE_RATE):
 def pred_ppg(whisper: WhisperB200, wavPath: str, ppgPath: str, device, mel_noise: Optional[List[torch.Tensor]] = None):
     audio = load_audio(wavPath)
     plan = chunk_plan(audio.shape[0])
-    mels = []
+    enc = whisper.encoder
+    nm = enc.cfg["n_mels"]
+    # chunks of equal length (all the full 15 s ones) form one batch; the remainder runs alone
+    groups: Dict[int, List[int]] = {}
     for i, (s, e, _) in enumerate(plan):
-        mel = log_mel_spectrogram(torch.from_numpy(audio[s:e]))
-        nz = mel_noise[i] if mel_noise is not None else torch.randn_like(mel)
-        mels.append(mel + nz * 0.1)  # whisper/inference.py:46,58
-    rows: List[np.ndarray] = []
-    # full 15 s chunks share a shape -> one batch; the remainder runs alone
-    full = [i for i, m in enumerate(mels) if m.shape[-1] == mels[0].shape[-1]]
+        groups.setdefault(e - s, []).append(i)
     outs: Dict[int, np.ndarray] = {}
-    if full:
-        o = whisper.encoder(torch.stack([mels[i] for i in full]))
-        for j, i in enumerate(full):
+    for n, idx in groups.items():
+        wav = torch.from_numpy(np.stack([audio[plan[i][0]:plan[i][1]] for i in idx]))
+        F = n // HOP_LENGTH
+        if mel_noise is not None:
+            nz = torch.stack([mel_noise[i] for i in idx])
+        else:  # host RNG like the reference's randn_like on the CPU mel (whisper/inference.py:46,58)
+            nz = torch.randn(len(idx), nm, F)
+        o = enc(enc.log_mel(wav, nz, 0.1))
+        for j, i in enumerate(idx):
             outs[i] = o[j].cpu().float().numpy()
-    for i, m in enumerate(mels):
-        if i not in outs:
-            outs[i] = whisper.encoder(m.unsqueeze(0))[0].cpu().float().numpy()
+    rows: List[np.ndarray] = []
     for i, (_, _, n_rows) in enumerate(plan):
         rows.extend(outs[i][:n_rows])
     np.save(ppgPath, np.asarray(rows), allow_pickle=False)
