@@ -18,6 +18,7 @@
 // sequence are kept at zero (= the convs' zero padding) and SnakeAlias clamps its taps to the
 // sequence (= its replicate padding), so tile edges reproduce the reference exactly.
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -31,16 +32,19 @@ __host__ __device__ inline int ab_halo(int K, const int* dil) {
   return h;
 }
 
-template <int C>
+template <int C, int V>
 struct AbCfg {
   static constexpr int CP = (C + 3) / 4 * 4;
   // The buffer width W (tile + both halos) is fixed so that the convolution's NT*THREADS time slots
   // are exactly filled (a 1216-wide buffer on 2x512 slots wasted 40 % of the FMA issue, r01 profile);
   // the number of output samples per CTA follows from the block's receptive field: TOUT = W - 2H.
-  static constexpr int THREADS = C <= 10 ? 512 : 384;
-  static constexpr int NT = 2;                           // time steps per thread in the convolution
-  static constexpr int W = NT * THREADS;                 // 1024 (C=10) / 768 (C=20)
-  static constexpr int ROWS8 = C <= 10 ? 8 : C;          // Snake rows done in 8-sample runs (rest: 4)
+  // Variant 1 trades threads for a taller register tile (NT x C accumulators per thread: every
+  // weight vector load then feeds NT*4 FMAs) — C=10: 3 x 512 slots (W=1536, also a smaller halo
+  // share), C=20: 3 x 256 (same W; shared memory holds no more).
+  static constexpr int THREADS = C <= 10 ? 512 : (V == 0 ? 384 : 256);
+  static constexpr int NT = V == 0 ? 2 : 3;              // time steps per thread in the convolution
+  static constexpr int W = NT * THREADS;                 // V0: 1024 (C=10) / 768 (C=20); V1: 1536 / 768
+  static constexpr int ROWS8 = (C <= 10 && V == 0) ? 8 : C;   // Snake rows done in 8-sample runs (rest: 4)
 };
 
 // SnakeAlias of src rows -> dst rows over buffer positions [0, W); lo_i / hi_i = first / last buffer
@@ -116,15 +120,15 @@ __device__ __forceinline__ void ab_snake_run(const float* __restrict__ xr, float
 // Rows [0, ROWS8) are covered by 8-sample runs and the remaining rows by 4-sample runs, chosen so
 // that both task counts are whole multiples of the CTA size (C=20: 20 rows x 96 runs = 5 x 384;
 // C=10: 8 x 128 = 2 x 512 and 2 x 256 = 512) — no partially filled pass.
-template <int C>
+template <int C, int V>
 __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* __restrict__ dst,
                                          const float* f_up, const float* f_dn, const float* ea,
                                          const float* ib, int lo_i, int hi_i, bool seq_lo, bool seq_hi, int tid) {
-  constexpr int AB_THREADS = AbCfg<C>::THREADS;
-  constexpr int W = AbCfg<C>::W, WS = W + 2 * AB_GUARD;
-  constexpr int ROWS8 = AbCfg<C>::ROWS8;
+  constexpr int AB_THREADS = AbCfg<C, V>::THREADS;
+  constexpr int W = AbCfg<C, V>::W, WS = W + 2 * AB_GUARD;
+  constexpr int ROWS8 = AbCfg<C, V>::ROWS8;
   constexpr int T8 = ROWS8 * (W / 8), T4 = (C - ROWS8) * (W / 4);
-  static_assert(T8 % AB_THREADS == 0 && T4 % AB_THREADS == 0, "Snake passes must be exactly filled");
+  static_assert(V != 0 || (T8 % AB_THREADS == 0 && T4 % AB_THREADS == 0), "Snake passes must be exactly filled");
   float fu[12], fdn[12];
 #pragma unroll
   for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }  // UpSample1d's ratio gain (resample.py:31)
@@ -140,13 +144,13 @@ __device__ __forceinline__ void ab_snake(const float* __restrict__ src, float* _
 
 // dst[co][t] = bias[co] + sum_ci sum_j w[ci][j][co] * src[ci][t + j*dil - P]  (+ dst[co][t] if RES);
 // a thread owns NT time steps (t + i*AB_THREADS) so every weight vector load feeds NT*C FMAs.
-template <int C, int K, bool RES>
+template <int C, int K, bool RES, int V>
 __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __restrict__ dst,
                                         const float* __restrict__ wsm, const float* __restrict__ bsm,
                                         int dil, int W, int WS, int lo_i, int hi_i, int tid) {
-  constexpr int CP = AbCfg<C>::CP;
-  constexpr int NT = AbCfg<C>::NT;
-  constexpr int AB_THREADS = AbCfg<C>::THREADS;
+  constexpr int CP = AbCfg<C, V>::CP;
+  constexpr int NT = AbCfg<C, V>::NT;
+  constexpr int AB_THREADS = AbCfg<C, V>::THREADS;
   const int P = dil * (K - 1) / 2;
   for (int tb = tid; tb < W; tb += NT * AB_THREADS) {
     float acc[NT][CP];
@@ -198,12 +202,12 @@ __device__ __forceinline__ void ab_conv(const float* __restrict__ src, float* __
   }
 }
 
-template <int C, int K>
-__global__ void __launch_bounds__(AbCfg<C>::THREADS, 1)
+template <int C, int K, int V>
+__global__ void __launch_bounds__(AbCfg<C, V>::THREADS, 1)
 amp_block_fused_kernel(const AmpBlockParams p) {
-  constexpr int AB_THREADS = AbCfg<C>::THREADS;
-  constexpr int CP = AbCfg<C>::CP;
-  constexpr int W = AbCfg<C>::W;
+  constexpr int AB_THREADS = AbCfg<C, V>::THREADS;
+  constexpr int CP = AbCfg<C, V>::CP;
+  constexpr int W = AbCfg<C, V>::W;
   extern __shared__ __align__(16) float ab_smem[];
   __shared__ float f_up[12], f_dn[12], s_ea[C], s_ib[C], s_bias[CP];
   const int tid = threadIdx.x;
@@ -245,10 +249,10 @@ amp_block_fused_kernel(const AmpBlockParams p) {
         wsm[i] = co < p.cout_pad ? __ldg(wg + (long long)cj * p.cout_pad + co) : 0.f;
       }
       __syncthreads();
-      ab_snake<C>(half == 0 ? X : Z, Y, f_up, f_dn, s_ea, s_ib, lo_i, hi_i, seq_lo, seq_hi, tid);
+      ab_snake<C, V>(half == 0 ? X : Z, Y, f_up, f_dn, s_ea, s_ib, lo_i, hi_i, seq_lo, seq_hi, tid);
       __syncthreads();
-      if (half == 0) ab_conv<C, K, false>(Y, Z, wsm, s_bias, p.dil[d], W, WS, lo_i, hi_i, tid);
-      else ab_conv<C, K, true>(Y, X, wsm, s_bias, 1, W, WS, lo_i, hi_i, tid);
+      if (half == 0) ab_conv<C, K, false, V>(Y, Z, wsm, s_bias, p.dil[d], W, WS, lo_i, hi_i, tid);
+      else ab_conv<C, K, true, V>(Y, X, wsm, s_bias, 1, W, WS, lo_i, hi_i, tid);
       __syncthreads();
     }
   }
@@ -267,17 +271,17 @@ amp_block_fused_kernel(const AmpBlockParams p) {
   }
 }
 
-template <int C, int K>
+template <int C, int K, int V>
 static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
-  constexpr int AB_THREADS = AbCfg<C>::THREADS;
+  constexpr int AB_THREADS = AbCfg<C, V>::THREADS;
   const int H = ab_halo(p.K, p.dil);
-  const int W = AbCfg<C>::W, WS = W + 2 * AB_GUARD, TOUT = W - 2 * H;
+  const int W = AbCfg<C, V>::W, WS = W + 2 * AB_GUARD, TOUT = W - 2 * H;
   if (TOUT < 64) { set_error("amp_block_fused: receptive field too large for the tile"); return SVCB_E_UNSUPPORTED; }
-  const size_t smem = ((size_t)3 * C * WS + (size_t)C * p.K * AbCfg<C>::CP) * sizeof(float);
+  const size_t smem = ((size_t)3 * C * WS + (size_t)C * p.K * AbCfg<C, V>::CP) * sizeof(float);
   if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
   static size_t attr_bytes = 0;
   if (smem > attr_bytes) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C, K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C, K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_bytes = smem;
   }
   dim3 grid((p.L + TOUT - 1) / TOUT, p.B);
@@ -285,7 +289,7 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);
   KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B + 6 * 70.0 * C * (double)p.L * p.B,
                  (p.accum ? 12.0 : 8.0) * C * (double)p.L * p.B);
-  amp_block_fused_kernel<C, K><<<grid, AB_THREADS, smem, s>>>(p);
+  amp_block_fused_kernel<C, K, V><<<grid, AB_THREADS, smem, s>>>(p);
   SVCB_LAUNCH_CHECK("amp_block_fused");
   return SVCB_OK;
 }
@@ -300,8 +304,14 @@ bool amp_block_fused_supported(int C, int K, const int* dil) {
 int launch_amp_block_fused(const AmpBlockParams& p, cudaStream_t s) {
   if (p.B <= 0 || p.L <= 0) return SVCB_OK;
   if (!amp_block_fused_supported(p.C, p.K, p.dil)) { set_error("amp_block_fused: unsupported channel count / reach"); return SVCB_E_UNSUPPORTED; }
-  if (p.C == 10) return p.K == 3 ? launch_ab<10, 3>(p, s) : p.K == 7 ? launch_ab<10, 7>(p, s) : launch_ab<10, 11>(p, s);
-  return p.K == 3 ? launch_ab<20, 3>(p, s) : p.K == 7 ? launch_ab<20, 7>(p, s) : launch_ab<20, 11>(p, s);
+  static const int variant = getenv("SVCB_AB_VARIANT") ? atoi(getenv("SVCB_AB_VARIANT")) : 1;  // measured: C=10 gains 9 % from the 3-step tile, C=20 nothing
+  const int v10 = variant & 1, v20 = (variant >> 1) & 1;
+  if (p.C == 10) {
+    if (v10) return p.K == 3 ? launch_ab<10, 3, 1>(p, s) : p.K == 7 ? launch_ab<10, 7, 1>(p, s) : launch_ab<10, 11, 1>(p, s);
+    return p.K == 3 ? launch_ab<10, 3, 0>(p, s) : p.K == 7 ? launch_ab<10, 7, 0>(p, s) : launch_ab<10, 11, 0>(p, s);
+  }
+  if (v20) return p.K == 3 ? launch_ab<20, 3, 1>(p, s) : p.K == 7 ? launch_ab<20, 7, 1>(p, s) : launch_ab<20, 11, 1>(p, s);
+  return p.K == 3 ? launch_ab<20, 3, 0>(p, s) : p.K == 7 ? launch_ab<20, 7, 0>(p, s) : launch_ab<20, 11, 0>(p, s);
 }
 
 }  // namespace svcb
