@@ -1,6 +1,6 @@
 // AMP-block link on the 5th-gen tensor cores, as two kernels that each stream at their own roofline:
 //
-//   snake_pack   SnakeAlias(x) -> bf16 hi/lo operand image in HBM            (CUDA cores, HBM-bound)
+//   snake_pack   SnakeAlias(x) -> bf16 hi/lo operand image in HBM            (CUDA cores, 8 B/element)
 //   amp_conv_tc  Conv1d(C->C, K, dilation) + bias (+residual, stage mean)    (tcgen05 + TMEM)
 //
 // Together they replace one `SnakeAlias -> Conv1d [-> + x]` link of AMPBlock.forward
@@ -17,7 +17,9 @@
 // panel layout of tc.cuh, the zero rows are the conv's zero padding, and every tap is the same
 // tile addressed through a row-shifted descriptor.
 #include <algorithm>
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "tc.cuh"
@@ -42,121 +44,115 @@ __device__ __forceinline__ float fast_sin(float x) {
 }
 
 // ------------------------------------------------------------------------------------ snake_pack
-// One CTA = 8 channels (one K-octet) x SP_TL image rows.  Three phases over shared memory:
-//  (a) x rows with a 6-sample halo, replicate-clamped at the sequence ends;
-//  (b) one work item per INPUT sample a: both up-sampled Snake values v[2a], v[2a+1] from the same
-//      7 inputs (12 FMA + 2 SFU sines), stored at vs[j], j = m - (2*n0 - 5);
-//  (c) one thread per pair of output rows: 14 consecutive v (4 x LDS.128) -> two 12-tap
-//      decimations per channel, bf16 hi/lo split, two 16-byte rows stored contiguously.
-// Only the first/last CTA of a sequence needs the replicate padding of v (fix-up pass).
-constexpr int SP_TL = 506;  // image rows per CTA: 506 + 6 = 512 up-sampling positions = 2 exact passes of 256 threads
-constexpr int SP_XW = SP_TL + 12;
-constexpr int SP_VW = 2 * SP_TL + 16;
+// Register-resident (same scheme as amp_block_fused's ab_snake_run; the earlier version staged x and
+// the 2x-rate Snake values of an 8 x 506 tile in shared memory across three CTA barriers and was
+// issue/latency-bound at 1.9 TB/s, profiles/r01_notes.md): no CTA barrier, no v buffer.  A warp owns one octet of
+// channels x 32 image rows: lane = 4*channel + run, a thread computes 8 consecutive samples of one
+// channel from the 24 inputs around them (six 16-byte loads), then the warp transposes its 8 x 32
+// tile through 1 KB of shared memory so that every lane packs ONE image row (8 channels -> 16 bytes
+// of bf16 hi and 16 of lo) and the warp stores 512 contiguous bytes per part.
+constexpr int SP3_ROWS = 256;  // image rows per CTA (8 warps x 32)
 
-__global__ void __launch_bounds__(256)
-snake_pack_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                  const float* __restrict__ ea, const float* __restrict__ inv_b,
-                  const float* __restrict__ fu, const float* __restrict__ fd, int C, int L, int Lp) {
-  extern __shared__ __align__(16) float sp_smem[];
-  float* xs = sp_smem;                 // [8][SP_XW]
-  float* vs = sp_smem + 8 * SP_XW;     // [8][SP_VW]
-  __shared__ float f_up[12], f_dn[12], s_ea[8], s_ib[8];
-  const int tid = threadIdx.x;
+template <bool VEC>
+__device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, int L, const float (&fu)[12],
+                                        const float (&fdn)[12], const float* f_up, const float* f_dn, float a_,
+                                        float b_, float (&o)[8]) {
+  // (the vector loads touch xr[n0-8 .. n0+16): keep them inside the row)
+  if (VEC ? (n0 - 8 >= 0 && n0 + 16 <= L) : (n0 - 6 >= 0 && n0 + 13 <= L - 1)) {
+    float x[24];  // xr[n0-8 .. n0+16)
+    if (VEC) {
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr + n0 - 8) + q);
+        x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
+      }
+    } else {
+#pragma unroll
+      for (int q = 2; q < 22; ++q) x[q] = __ldg(xr + n0 - 8 + q);
+    }
+    float vv[28];
+#pragma unroll
+    for (int p = 0; p < 14; ++p) {
+      float ue = x[p + 2] * fu[11];
+      ue = fmaf(x[p + 3], fu[9], ue); ue = fmaf(x[p + 4], fu[7], ue); ue = fmaf(x[p + 5], fu[5], ue);
+      ue = fmaf(x[p + 6], fu[3], ue); ue = fmaf(x[p + 7], fu[1], ue);
+      float uo = x[p + 3] * fu[10];
+      uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
+      uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
+      const float se = __sinf(ue * a_), so = __sinf(uo * a_);   // fu carries UpSample1d's x2 gain
+      vv[2 * p] = fmaf(b_, se * se, ue);
+      vv[2 * p + 1] = fmaf(b_, so * so, uo);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 12; ++k) acc = fmaf(vv[2 * i + 1 + k], fdn[k], acc);
+      o[i] = acc;
+    }
+  } else {  // a tap crosses a sequence end: replicate-clamped scalar path; rows outside [0, L) are zero
+    const int mhi = 2 * L - 1;
+    for (int i = 0; i < 8; ++i) {
+      const int n = n0 + i;
+      float acc = 0.f;
+      if (n >= 0 && n < L) {
+        for (int k = 0; k < 12; ++k) {
+          const int m = min(max(2 * n - 5 + k, 0), mhi);
+          const int a = m >> 1, q = m & 1;
+          float u = 0.f;
+          for (int d = q; d < q + 6; ++d) u = fmaf(__ldg(xr + min(max(a - 3 + d, 0), L - 1)), f_up[11 + q - 2 * d], u);
+          u *= 2.f;
+          const float sn = __sinf(u * a_);
+          acc = fmaf(fmaf(b_, sn * sn, u), f_dn[k], acc);
+        }
+      }
+      o[i] = acc;
+    }
+  }
+}
+
+template <bool VEC, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+snake_pack3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                   const float* __restrict__ ea, const float* __restrict__ inv_b,
+                   const float* __restrict__ fu_g, const float* __restrict__ fd_g, int C, int L, int Lp) {
+  __shared__ float tile[8][32 * 9];   // per warp: [row][channel], row stride 9 -> conflict-free both ways
+  __shared__ float f_up[12], f_dn[12];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int oc = blockIdx.y, b = blockIdx.z;
-  const int row0 = blockIdx.x * SP_TL;  // first image row of this CTA
-  const int n0 = row0 - P8_PAD;         // its sequence position
-  const int nvalid = min(8, C - oc * 8);
-  if (tid < 12) { f_up[tid] = __ldg(fu + tid); f_dn[tid] = __ldg(fd + tid); }
-  if (tid >= 32 && tid < 32 + 8 && tid - 32 < nvalid) {
-    s_ea[tid - 32] = __ldg(ea + oc * 8 + tid - 32);
-    s_ib[tid - 32] = __ldg(inv_b + oc * 8 + tid - 32);
-  }
-  const long long img = ((long long)b * gridDim.y + oc) * Lp;
-  const bool any = n0 < L && n0 + SP_TL > 0 && nvalid > 0;  // block-uniform
-  const int mbase = 2 * n0 - 5;
-  if (any) {
-    const float* xb = x + ((long long)b * C + oc * 8) * L;
-    for (int idx = tid; idx < nvalid * SP_XW; idx += 256) {   // flat over (channel, position)
-      const int c = idx / SP_XW, i = idx - c * SP_XW;
-      const int g = min(max(n0 - 6 + i, 0), L - 1);
-      xs[idx] = __ldg(xb + (long long)c * L + g);
-    }
-    __syncthreads();
-    static_assert(SP_TL + 6 == 512, "phase (b) indexing assumes 512 up-sampling positions per channel");
-    for (int idx = tid; idx < nvalid * 512; idx += 256) {     // flat over (channel, a - n0 + 3)
-      const int c = idx >> 9, ar = (idx & 511) - 3;
-      const float a_ = s_ea[c], ib = s_ib[c];
-      const float* xp = xs + c * SP_XW + ar + 6;
-      float* vc = vs + c * SP_VW;
-      const float xm3 = xp[-3], xm2 = xp[-2], xm1 = xp[-1], x0 = xp[0], x1 = xp[1], x2 = xp[2], x3 = xp[3];
-      float ue = xm3 * f_up[11];
-      ue = fmaf(xm2, f_up[9], ue); ue = fmaf(xm1, f_up[7], ue); ue = fmaf(x0, f_up[5], ue);
-      ue = fmaf(x1, f_up[3], ue); ue = fmaf(x2, f_up[1], ue);
-      float uo = xm2 * f_up[10];
-      uo = fmaf(xm1, f_up[8], uo); uo = fmaf(x0, f_up[6], uo); uo = fmaf(x1, f_up[4], uo);
-      uo = fmaf(x2, f_up[2], uo); uo = fmaf(x3, f_up[0], uo);
-      ue *= 2.f; uo *= 2.f;
-      const float se = __sinf(ue * a_), so = __sinf(uo * a_);
-      const int j = 2 * ar + 5;
-      if (j >= 0) vc[j] = fmaf(ib, se * se, ue);
-      vc[j + 1] = fmaf(ib, so * so, uo);
-    }
-    __syncthreads();
-    if (mbase < 0 || mbase + 2 * SP_TL + 10 > 2 * L) {  // replicate padding of v at the sequence ends
-      const int jlo = -mbase, jhi = 2 * L - 1 - mbase;   // positions of v[0] and v[2L-1]
-      for (int c = 0; c < nvalid; ++c) {
-        float* vc = vs + c * SP_VW;
-        for (int j = tid; j < 2 * SP_TL + 12; j += 256) {
-          if (j < jlo) vc[j] = vc[jlo];
-          else if (j > jhi && jhi >= 0) vc[j] = vc[jhi];
-        }
-      }
-      __syncthreads();
-    }
-  }
-  // (c) rows 2*tid, 2*tid+1
-  {
-    const int r = 2 * tid;
-    const int row = row0 + r;
-    if (r < SP_TL && row < Lp) {
-      const int tau = n0 + r;
-      __align__(16) __nv_bfloat162 h2[8], l2[8];  // [row parity*4 + channel pair]
-      float prev0 = 0.f, prev1 = 0.f;
+  if (tid < 12) { f_up[tid] = __ldg(fu_g + tid); f_dn[tid] = __ldg(fd_g + tid); }
+  __syncthreads();
+  const int row0 = blockIdx.x * SP3_ROWS + warp * 32;   // first image row of this warp
+  if (row0 >= Lp) return;                               // warp-uniform
+  const int c = lane >> 2, run = lane & 3;
+  const int ch = oc * 8 + c;
+  const int n0 = row0 - P8_PAD + 8 * run;
+  float o[8];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        float o0 = 0.f, o1 = 0.f;
-        if (any && c < nvalid && tau + 1 >= 0 && tau < L) {
-          const float4* vp = reinterpret_cast<const float4*>(vs + c * SP_VW + 2 * r);
-          const float4 q0 = vp[0], q1 = vp[1], q2 = vp[2], q3 = vp[3];
-          const float w[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w,
-                               q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+  for (int i = 0; i < 8; ++i) o[i] = 0.f;
+  if (ch < C && n0 < L && n0 + 8 > 0) {
+    float fu[12], fdn[12];
 #pragma unroll
-          for (int k = 0; k < 12; ++k) { o0 = fmaf(w[k], f_dn[k], o0); o1 = fmaf(w[k + 2], f_dn[k], o1); }
-          if (tau < 0) o0 = 0.f;
-          if (tau + 1 >= L) o1 = 0.f;
-        }
-        if (c & 1) {  // one packed conversion per channel pair and row
-          const __nv_bfloat162 ha = __floats2bfloat162_rn(prev0, o0), hb = __floats2bfloat162_rn(prev1, o1);
-          const float2 fa = __bfloat1622float2(ha), fb = __bfloat1622float2(hb);
-          h2[c >> 1] = ha; h2[4 + (c >> 1)] = hb;
-          l2[c >> 1] = __floats2bfloat162_rn(prev0 - fa.x, o0 - fa.y);
-          l2[4 + (c >> 1)] = __floats2bfloat162_rn(prev1 - fb.x, o1 - fb.y);
-        } else {
-          prev0 = o0; prev1 = o1;
-        }
-      }
-      const __nv_bfloat162* h8 = h2;
-      const __nv_bfloat162* l8 = l2;
-      uint4* dh = reinterpret_cast<uint4*>(hi + (img + row) * 8);
-      dh[0] = *reinterpret_cast<const uint4*>(h8);
-      dh[1] = *reinterpret_cast<const uint4*>(h8 + 4);
-      if (lo) {
-        uint4* dl = reinterpret_cast<uint4*>(lo + (img + row) * 8);
-        dl[0] = *reinterpret_cast<const uint4*>(l8);
-        dl[1] = *reinterpret_cast<const uint4*>(l8 + 4);
-      }
-    }
+    for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }
+    sp3_run<VEC>(x + ((long long)b * C + ch) * L, n0, L, fu, fdn, f_up, f_dn, __ldg(ea + ch), __ldg(inv_b + ch), o);
   }
+  float* tw = tile[warp];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tw[(8 * run + i) * 9 + c] = o[i];
+  __syncwarp();
+  float r[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) r[k] = tw[lane * 9 + k];
+  __align__(16) __nv_bfloat162 h2[4], l2[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    h2[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+    const float2 f = __bfloat1622float2(h2[k]);
+    l2[k] = __floats2bfloat162_rn(r[2 * k] - f.x, r[2 * k + 1] - f.y);
+  }
+  const long long img = ((long long)b * gridDim.y + oc) * Lp + row0 + lane;
+  *reinterpret_cast<uint4*>(hi + img * 8) = *reinterpret_cast<const uint4*>(h2);
+  if (lo) *reinterpret_cast<uint4*>(lo + img * 8) = *reinterpret_cast<const uint4*>(l2);
 }
 
 size_t p8_image_bytes(int B, int C, int L) {  // one of hi / lo
@@ -168,19 +164,20 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
                       const float* fd, int B, int C, int L, cudaStream_t s) {
   if (B <= 0 || C <= 0 || L <= 0) return SVCB_OK;
   const int cp = (C + 15) / 16 * 16, Lp = p8_rows_of(L);
-  const size_t smem = (size_t)(8 * SP_XW + 8 * SP_VW) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(snake_pack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
-  dim3 grid((Lp + SP_TL - 1) / SP_TL, cp / 8, B);
   char kname[64];
   snprintf(kname, sizeof(kname), "snake_pack_c%d", C);
   KernelScope ks(kname, s, 70.0 * B * C * (double)L, (lo ? 8.0 : 6.0) * B * C * (double)L);
-  snake_pack_kernel<<<grid, 256, smem, s>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ea,
-                                            inv_b, fu, fd, C, L, Lp);
-  SVCB_LAUNCH_CHECK("snake_pack");
+  {
+    dim3 grid3((Lp + SP3_ROWS - 1) / SP3_ROWS, cp / 8, B);
+    auto* h = static_cast<__nv_bfloat16*>(hi);
+    auto* l = static_cast<__nv_bfloat16*>(lo);
+    const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    // 64 registers -> four CTAs (32 warps) per SM: each warp lives for one tile, so residency is
+    // what hides its initial load latency (10.8 vs 11.4 ms/step with two CTAs)
+    if (vec) snake_pack3_kernel<true, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, C, L, Lp);
+    else snake_pack3_kernel<false, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, C, L, Lp);
+    SVCB_LAUNCH_CHECK("snake_pack");
+  }
   return SVCB_OK;
 }
 

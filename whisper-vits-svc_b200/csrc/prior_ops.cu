@@ -89,13 +89,14 @@ __global__ void __launch_bounds__(256)
 rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek,
                      const float* __restrict__ ev, const long long* __restrict__ lengths,
                      float* __restrict__ out, int H, int heads, int window, int T) {
-  constexpr int DP = D + 1;
-  extern __shared__ float sm[];
+  constexpr int DP = D + 4;          // row stride of Q/K tiles: 16-byte rows, conflict-free LDS.128 over 8 rows
+  constexpr int SP = RA_BK + 4;      // row stride of the score tile
+  extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                      // [64][DP]  (also output staging)
   float* Ks = Qs + RA_BQ * DP;         // [64][DP]
   float* Vs = Ks + RA_BK * DP;         // [64][D]
-  float* Ss = Vs + RA_BK * D;          // [64][65]
-  float* Ek = Ss + RA_BQ * (RA_BK + 1);// [2w+1][D]
+  float* Ss = Vs + RA_BK * D;          // [64][SP]
+  float* Ek = Ss + RA_BQ * SP;         // [2w+1][D]
   float* Ev = Ek + (2 * window + 1) * D;
   float* Rk = Ev + (2 * window + 1) * D;  // [64][2w+1]
   float* row_m = Rk + RA_BQ * (2 * window + 1);
@@ -151,16 +152,21 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
     for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) sacc[ii][jj] = 0.f;
-    for (int d = 0; d < D; ++d) {
-      float qv[4], kv[4];
+    for (int d = 0; d < D; d += 4) {   // four head-dim columns per 16-byte shared load
+      float4 qv[4], kv[4];
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii) qv[ii] = Qs[(ty + 16 * ii) * DP + d];
+      for (int ii = 0; ii < 4; ++ii) qv[ii] = *reinterpret_cast<const float4*>(Qs + (ty + 16 * ii) * DP + d);
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) kv[jj] = Ks[(tx + 16 * jj) * DP + d];
+      for (int jj = 0; jj < 4; ++jj) kv[jj] = *reinterpret_cast<const float4*>(Ks + (tx + 16 * jj) * DP + d);
 #pragma unroll
       for (int ii = 0; ii < 4; ++ii)
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) sacc[ii][jj] = fmaf(qv[ii], kv[jj], sacc[ii][jj]);
+        for (int jj = 0; jj < 4; ++jj) {
+          float a = sacc[ii][jj];
+          a = fmaf(qv[ii].x, kv[jj].x, a); a = fmaf(qv[ii].y, kv[jj].y, a);
+          a = fmaf(qv[ii].z, kv[jj].z, a); a = fmaf(qv[ii].w, kv[jj].w, a);
+          sacc[ii][jj] = a;
+        }
     }
 #pragma unroll
     for (int ii = 0; ii < 4; ++ii) {
@@ -173,7 +179,7 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
         if (rel >= -window && rel <= window) sv += Rk[i * nrel + rel + window];
         if (ig >= len || jg >= len) sv = -1e4f;
         if (jg >= T) sv = -INFINITY;
-        Ss[i * (RA_BK + 1) + j] = sv;
+        Ss[i * SP + j] = sv;
       }
     }
     __syncthreads();
@@ -182,7 +188,7 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
       const int w = tid >> 5, lane = tid & 31;
       for (int rr = 0; rr < 8; ++rr) {
         const int i = w * 8 + rr;
-        float s0 = Ss[i * (RA_BK + 1) + lane], s1 = Ss[i * (RA_BK + 1) + lane + 32];
+        float s0 = Ss[i * SP + lane], s1 = Ss[i * SP + lane + 32];
         float mx = fmaxf(s0, s1);
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
@@ -192,8 +198,8 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
         float ps = p0 + p1;
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, off);
-        Ss[i * (RA_BK + 1) + lane] = p0;
-        Ss[i * (RA_BK + 1) + lane + 32] = p1;
+        Ss[i * SP + lane] = p0;
+        Ss[i * SP + lane + 32] = p1;
         if (lane == 0) {
           const float alpha = expf(m_old - m_new);  // exp(-inf) = 0 on the first tile
           row_a[i] = alpha;
@@ -211,16 +217,25 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
 #pragma unroll
       for (int dd = 0; dd < ND; ++dd) o[ii][dd] *= al;
     }
-    for (int j = 0; j < RA_BK; ++j) {
-      float pv[4], vv[ND];
+    for (int j = 0; j < RA_BK; j += 4) {   // a thread owns head-dim columns ND*tx .. ND*tx+ND-1
+      float4 pv[4];
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii) pv[ii] = Ss[(ty + 16 * ii) * (RA_BK + 1) + j];
+      for (int ii = 0; ii < 4; ++ii) pv[ii] = *reinterpret_cast<const float4*>(Ss + (ty + 16 * ii) * SP + j);
 #pragma unroll
-      for (int dd = 0; dd < ND; ++dd) vv[dd] = Vs[j * D + tx + 16 * dd];
+      for (int jj = 0; jj < 4; ++jj) {
+        float vv[ND];
 #pragma unroll
-      for (int ii = 0; ii < 4; ++ii)
+        for (int dd = 0; dd < ND; dd += 2) {
+          const float2 t2 = *reinterpret_cast<const float2*>(Vs + (j + jj) * D + ND * tx + dd);
+          vv[dd] = t2.x; vv[dd + 1] = t2.y;
+        }
 #pragma unroll
-        for (int dd = 0; dd < ND; ++dd) o[ii][dd] = fmaf(pv[ii], vv[dd], o[ii][dd]);
+        for (int ii = 0; ii < 4; ++ii) {
+          const float pj = jj == 0 ? pv[ii].x : jj == 1 ? pv[ii].y : jj == 2 ? pv[ii].z : pv[ii].w;
+#pragma unroll
+          for (int dd = 0; dd < ND; ++dd) o[ii][dd] = fmaf(pj, vv[dd], o[ii][dd]);
+        }
+      }
     }
     if (band) {
 #pragma unroll
@@ -229,9 +244,9 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
         for (int rr = 0; rr < nrel; ++rr) {
           const int jg = ig + rr - window;
           if (jg < j0 || jg >= j0 + RA_BK || jg >= T || jg < 0) continue;
-          const float pr = Ss[i * (RA_BK + 1) + (jg - j0)];
+          const float pr = Ss[i * SP + (jg - j0)];
 #pragma unroll
-          for (int dd = 0; dd < ND; ++dd) o[ii][dd] = fmaf(pr, Ev[rr * D + tx + 16 * dd], o[ii][dd]);
+          for (int dd = 0; dd < ND; ++dd) o[ii][dd] = fmaf(pr, Ev[rr * D + ND * tx + dd], o[ii][dd]);
         }
       }
     }
@@ -243,7 +258,7 @@ rel_attention_kernel(const float* __restrict__ qkv, const float* __restrict__ ek
     const int i = ty + 16 * ii;
     const float inv = 1.f / row_l[i];
 #pragma unroll
-    for (int dd = 0; dd < ND; ++dd) Qs[i * DP + tx + 16 * dd] = o[ii][dd] * inv;
+    for (int dd = 0; dd < ND; ++dd) Qs[i * DP + ND * tx + dd] = o[ii][dd] * inv;
   }
   __syncthreads();
   float* ob = out + ((long long)b * H + (long long)h * D) * T;
@@ -263,7 +278,7 @@ int launch_rel_attention(const float* qkv, const float* ek, const float* ev,
     return SVCB_E_UNSUPPORTED;
   }
   const int nrel = 2 * window + 1;
-  const size_t smem = (size_t)(RA_BQ * (D + 1) + RA_BK * (D + 1) + RA_BK * D + RA_BQ * (RA_BK + 1) +
+  const size_t smem = (size_t)(RA_BQ * (D + 4) + RA_BK * (D + 4) + RA_BK * D + RA_BQ * (RA_BK + 4) +
                                2 * nrel * D + RA_BQ * nrel + 3 * RA_BQ) * sizeof(float);
   static bool attr = false;
   if (!attr) {
