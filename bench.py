@@ -300,6 +300,15 @@ def run_ours(args, hp, sd):
             peak = peaks["hbm"]
             roof = {"kernel": top["name"], "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s",
                     "frac": ach / peak, "traffic": None}
+        try:  # measured DRAM traffic of this family (ncu --set full capture committed under profiles/)
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as tf:
+                tr = json.load(tf).get(top["name"])
+            if tr:
+                roof["traffic"] = tr["bytes_per_launch"]
+                roof["traffic_unit"] = "bytes per launch (dram read+write, " + tr["source"] + ")"
+                roof["algorithmic_bytes_per_launch"] = round(top["bytes"] / max(top["launches"], 1))
+        except (OSError, ValueError, KeyError):
+            pass
         roof["intensity_flop_per_byte"] = round(intensity, 1)
         roof["peak_source"] = f"of {peaks['src']} (MEASURED_PEAKS.json sustained bf16 / copy bandwidth)"
         roof["how"] = (f"CUDA events around every launch of this kernel over {args.steps} steps identical to the "
