@@ -198,6 +198,7 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = tc::warp_uniform_idx();
   const int P = p.dil * (p.K - 1) / 2;
   const int R = TC_M + (p.K - 1) * p.dil;
   const int KC = p.Cp / 8;
@@ -257,8 +258,9 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
         }
       }
     }
-  } else if (tid == 288) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp_u == 9) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp, uniform
+    // control flow; one elected lane issues — see tc::elect_one)
     const uint32_t idesc = tc::idesc_bf16(TC_M, p.Cp);
     const uint32_t a0 = tc::smem_u32(Abase), w0 = tc::smem_u32(Wbase);
     const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.Cp * 16u;
@@ -292,21 +294,28 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
           }
           const uint64_t bd0 = tc::smem_desc(wbase, lbo_b);
           const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
-          for (int ap = 0; ap < n_a; ++ap) {
-            uint64_t ad = (ap == 0 ? ad_hi0 : ad_lo0) + tap_off;
-            uint64_t bd = bd0;
-            for (int kk = 0; kk < nk; ++kk) {
-              tc::mma_bf16(d_tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
-              ad += kstep_a;
-              bd += kstep_b;
+          if (tc::elect_one()) {
+            uint32_t acc_flag = accumulate;
+            for (int ap = 0; ap < n_a; ++ap) {
+              uint64_t ad = (ap == 0 ? ad_hi0 : ad_lo0) + tap_off;
+              uint64_t bd = bd0;
+              for (int kk = 0; kk < nk; ++kk) {
+                tc::mma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+                acc_flag = 1;
+                ad += kstep_a;
+                bd += kstep_b;
+              }
             }
+            if (!resident) tc::mma_commit(&w_empty[st]);
           }
-          if (!resident) { tc::mma_commit(&w_empty[st]); ++wi; }
+          accumulate = 1;
+          if (!resident) ++wi;
         }
       }
-      tc::mma_commit(&a_empty[buf]);
-      tc::mma_commit(&t_full[acc]);
+      if (tc::elect_one()) {
+        tc::mma_commit(&a_empty[buf]);
+        tc::mma_commit(&t_full[acc]);
+      }
     }
   } else if (warp < 8) {
     // ---------------------------------------------------------------- epilogue

@@ -46,6 +46,7 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[CT_WST], w_empty[CT_WST], bar_acc;
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int warp_u = tc::warp_uniform_idx();
   const int b = blockIdx.z, nt = blockIdx.y;
   const int t0 = blockIdx.x * CT_M;
   const int P = p.pad;
@@ -186,8 +187,9 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
       tc::mbar_arrive_expect_tx(&w_full[st], w_tile);
       tc::bulk_g2s(W0 + (size_t)st * w_tile, p.wpk + tile * w_tile, w_tile, &w_full[st]);
     }
-  } else if (tid == 160) {
-    // ---------------------------------------------------------------- MMA issuer
+  } else if (warp_u == 5) {
+    // ---------------------------------------------------------------- MMA issuer (whole warp walks the
+    // uniform loop, one elected lane issues: tc::elect_one)
     const uint32_t idesc = tc::idesc_bf16(CT_M, p.bn);
     const uint32_t a_base = tc::smem_u32(A0), w_base = tc::smem_u32(W0);
     const uint32_t lbo_a = (uint32_t)R * 16u, lbo_b = (uint32_t)p.bn * 16u;
@@ -208,22 +210,26 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
           tc::fence_after_sync();
           const uint64_t bd0 = tc::smem_desc(w_base + (uint32_t)st * w_tile, lbo_b);
           const int n_a = (part == 0 && nparts == 2) ? 2 : 1;
-          for (int ap = 0; ap < n_a; ++ap) {
-            uint64_t ad = tc::smem_desc((ap == 0 ? ah : al) + row_off, lbo_a);
-            uint64_t bd = bd0;
-            for (int kk = 0; kk < nk; ++kk) {
-              tc::mma_bf16(tmem, ad, bd, idesc, accumulate);
-              accumulate = 1;
-              ad += kstep_a;
-              bd += kstep_b;
+          if (tc::elect_one()) {
+            uint32_t acc_flag = accumulate;
+            for (int ap = 0; ap < n_a; ++ap) {
+              uint64_t ad = tc::smem_desc((ap == 0 ? ah : al) + row_off, lbo_a);
+              uint64_t bd = bd0;
+              for (int kk = 0; kk < nk; ++kk) {
+                tc::mma_bf16(tmem, ad, bd, idesc, acc_flag);
+                acc_flag = 1;
+                ad += kstep_a;
+                bd += kstep_b;
+              }
             }
+            tc::mma_commit(&w_empty[st]);
           }
-          tc::mma_commit(&w_empty[st]);
+          accumulate = 1;
         }
       }
-      tc::mma_commit(&a_empty[buf]);
+      if (tc::elect_one()) tc::mma_commit(&a_empty[buf]);
     }
-    tc::mma_commit(&bar_acc);
+    if (tc::elect_one()) tc::mma_commit(&bar_acc);
   }
   tc::fence_before_sync();
   __syncthreads();

@@ -116,6 +116,16 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// One lane of a fully active warp (the same lane every time for the same mask).  Used as
+// `if (elect_one()) { tcgen05.mma ...; tcgen05.commit ... }` inside WARP-UNIFORM control flow
+// (branch on warp_uniform_idx()): descriptors and loop state then live in uniform registers and the
+// MMA issues without the per-instruction R2UR + ELECT waterfall a `tid == X` branch compiles to.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.b32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ int warp_uniform_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
 // all previously issued MMAs of this thread arrive on `bar` when complete (implies fence::before)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
