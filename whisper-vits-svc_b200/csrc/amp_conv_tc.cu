@@ -296,11 +296,12 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
           const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
           if (tc::elect_one()) {
             uint32_t acc_flag = accumulate;
+            const uint32_t a_hiw = (uint32_t)(ad_hi0 >> 32), b_hiw = (uint32_t)(bd0 >> 32);
             for (int ap = 0; ap < n_a; ++ap) {
-              uint64_t ad = (ap == 0 ? ad_hi0 : ad_lo0) + tap_off;
-              uint64_t bd = bd0;
+              uint32_t ad = (uint32_t)(ap == 0 ? ad_hi0 : ad_lo0) + tap_off;   // low words: start-address field
+              uint32_t bd = (uint32_t)bd0;
               for (int kk = 0; kk < nk; ++kk) {
-                tc::mma_bf16(d_tmem, ad, bd, idesc, acc_flag);
+                tc::mma_bf16_lohi(d_tmem, ad, a_hiw, bd, b_hiw, idesc, acc_flag);
                 acc_flag = 1;
                 ad += kstep_a;
                 bd += kstep_b;

@@ -212,11 +212,13 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
           const int n_a = (part == 0 && nparts == 2) ? 2 : 1;
           if (tc::elect_one()) {
             uint32_t acc_flag = accumulate;
+            const uint32_t b_hiw = (uint32_t)(bd0 >> 32);
             for (int ap = 0; ap < n_a; ++ap) {
-              uint64_t ad = tc::smem_desc((ap == 0 ? ah : al) + row_off, lbo_a);
-              uint64_t bd = bd0;
+              const uint64_t ad0 = tc::smem_desc((ap == 0 ? ah : al) + row_off, lbo_a);
+              const uint32_t a_hiw = (uint32_t)(ad0 >> 32);
+              uint32_t ad = (uint32_t)ad0, bd = (uint32_t)bd0;   // low words: only the start-address field moves
               for (int kk = 0; kk < nk; ++kk) {
-                tc::mma_bf16(tmem, ad, bd, idesc, acc_flag);
+                tc::mma_bf16_lohi(tmem, ad, a_hiw, bd, b_hiw, idesc, acc_flag);
                 acc_flag = 1;
                 ad += kstep_a;
                 bd += kstep_b;

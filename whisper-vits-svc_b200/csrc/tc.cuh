@@ -116,6 +116,23 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
       : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// The same MMA with the two descriptors given as (low, high) words: only the low word (start address
+// field) changes from one MMA to the next, so the issue loop advances it with ONE 32-bit add per
+// operand and the constant high words stay put (a 64-bit add + two register-to-uniform moves per
+// operand per MMA is what bounded the narrow-N issue rate at ~118 cycles per instruction).
+__device__ __forceinline__ void mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                              uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // One lane of a fully active warp (the same lane every time for the same mask).  Used as
 // `if (elect_one()) { tcgen05.mma ...; tcgen05.commit ... }` inside WARP-UNIFORM control flow
 // (branch on warp_uniform_idx()): descriptors and loop state then live in uniform registers and the
