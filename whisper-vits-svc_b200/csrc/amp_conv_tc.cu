@@ -188,11 +188,11 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 //                    (all taps resident in shared memory when they fit, else a 2-slot ring per tile)
 //   MMA thread       all taps x split parts of tile i into TMEM accumulator (i & 1)
 //   4 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
-struct AmpPlan { int resident, nabuf, acc_stride, ncols; size_t smem; };
+struct AmpPlan { int resident, nabuf, acc_stride, ncols, ncat; size_t smem; };
 
 __global__ void __launch_bounds__(320, 1)
 amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, const int acc_stride,
-                   const uint32_t ncols) {
+                   const uint32_t ncols, const int ncat) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[2], w_empty[2], w_res, t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
@@ -230,10 +230,25 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
 
   if (tid == 256) {
     // ---------------------------------------------------------------- producer
+    // ncat: the hi and lo weight tiles of a tap are interleaved per K-chunk ([kc][hi rows | lo rows][8])
+    // so that ONE descriptor with N = 2*Cp multiplies A_hi by [W_hi | W_lo]; the hi-only view of the
+    // same bytes (N = Cp, same stride) serves A_lo * W_hi.  The packed blob keeps its layout: the
+    // interleave happens here, one bulk copy per (tap, part, K-chunk).
+    const uint32_t wrow = (uint32_t)p.Cp * 16u;   // one K-chunk of one part
+    auto load_tap_cat = [&](uint8_t* dst, int tap, uint64_t* bar) {
+      for (int part = 0; part < 2; ++part)
+        for (int kc = 0; kc < KC; ++kc)
+          tc::bulk_g2s(dst + (size_t)kc * 2 * wrow + (size_t)part * wrow,
+                       p.wpk + ((size_t)tap * 2 + part) * wb + (size_t)kc * wrow, wrow, bar);
+    };
     if (resident) {
       tc::mbar_arrive_expect_tx(&w_res, wb * (uint32_t)nch);
-      for (int i = 0; i < nch; ++i)
-        tc::bulk_g2s(Wbase + (size_t)i * wb, p.wpk + ((size_t)(i / parts) * 2 + (i % parts)) * wb, wb, &w_res);
+      if (ncat) {
+        for (int tap = 0; tap < p.K; ++tap) load_tap_cat(Wbase + (size_t)tap * 2 * wb, tap, &w_res);
+      } else {
+        for (int i = 0; i < nch; ++i)
+          tc::bulk_g2s(Wbase + (size_t)i * wb, p.wpk + ((size_t)(i / parts) * 2 + (i % parts)) * wb, wb, &w_res);
+      }
     }
     const uint32_t run = (uint32_t)R * 16u;
     int it = 0, wi = 0;
@@ -249,7 +264,14 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
         for (int kc = 0; kc < KC; ++kc)
           tc::bulk_g2s(dst + (size_t)kc * run, src + (((long long)b * KC + kc) * p.Lp + row) * 16, run, &a_full[buf]);
       }
-      if (!resident) {
+      if (!resident && ncat) {
+        for (int tap = 0; tap < p.K; ++tap, ++wi) {
+          const int st = wi & 1;
+          if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          tc::mbar_arrive_expect_tx(&w_full[st], 2 * wb);
+          load_tap_cat(Wbase + (size_t)st * 2 * wb, tap, &w_full[st]);
+        }
+      } else if (!resident) {
         for (int i = 0; i < nch; ++i, ++wi) {
           const int st = wi & 1;
           if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
@@ -279,7 +301,49 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
       const int nk = p.Cp / 16;
       uint32_t accumulate = 0;
       int i = 0;
-      for (int tap = 0; tap < p.K; ++tap) {
+      if (ncat) {
+        // two MMA groups per tap instead of three: A_hi x [W_hi | W_lo] (N = 2*Cp, columns [0,Cp) and
+        // [Cp,2Cp) of the accumulator) and A_lo x W_hi (N = Cp, into columns [0,Cp)); the epilogue adds
+        // the two column halves.  An MMA costs ~110 cycles here whatever its N (r01 captures), so the
+        // instruction count is what matters.
+        const uint32_t idesc_cat = tc::idesc_bf16(TC_M, 2 * p.Cp);
+        const uint32_t lbo_c = 2u * lbo_b, kstep_c = (2u * lbo_c) >> 4;
+        for (int tap = 0; tap < p.K; ++tap) {
+          const uint32_t tap_off = (uint32_t)(tap * p.dil);
+          uint32_t wbase;
+          int st = 0;
+          if (resident) {
+            wbase = w0 + (uint32_t)tap * 2u * wb;
+          } else {
+            st = wi & 1;
+            tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+            tc::fence_after_sync();
+            wbase = w0 + (uint32_t)st * 2u * wb;
+          }
+          const uint64_t bd0 = tc::smem_desc(wbase, lbo_c);
+          if (tc::elect_one()) {
+            uint32_t acc_flag = accumulate;
+            const uint32_t a_hiw = (uint32_t)(ad_hi0 >> 32), b_hiw = (uint32_t)(bd0 >> 32);
+            uint32_t ad = (uint32_t)ad_hi0 + tap_off, bd = (uint32_t)bd0;
+            for (int kk = 0; kk < nk; ++kk) {
+              tc::mma_bf16_lohi(d_tmem, ad, a_hiw, bd, b_hiw, idesc_cat, acc_flag);
+              acc_flag = 1;
+              ad += kstep_a;
+              bd += kstep_c;
+            }
+            ad = (uint32_t)ad_lo0 + tap_off; bd = (uint32_t)bd0;
+            for (int kk = 0; kk < nk; ++kk) {
+              tc::mma_bf16_lohi(d_tmem, ad, a_hiw, bd, b_hiw, idesc, 1u);
+              ad += kstep_a;
+              bd += kstep_c;
+            }
+            if (!resident) tc::mma_commit(&w_empty[st]);
+          }
+          accumulate = 1;
+          if (!resident) ++wi;
+        }
+      }
+      for (int tap = 0; tap < (ncat ? 0 : p.K); ++tap) {
         const uint32_t tap_off = (uint32_t)(tap * p.dil);  // rows -> 16-byte units
         for (int part = 0; part < parts; ++part, ++i) {
           uint32_t wbase;
@@ -353,10 +417,15 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
       tc::fence_after_sync();
       const uint32_t tbase = tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)(acc * acc_stride);
       for (int strip = grp; strip < nstrips; strip += 2) {
-        uint32_t v[16];
+        uint32_t v[16], v2[16];
         tc::tmem_ld16(tbase + (uint32_t)(strip * 16), v);
+        if (ncat) tc::tmem_ld16(tbase + (uint32_t)(p.Cp + strip * 16), v2);   // the A_hi x W_lo half
         if (strip + 2 < nstrips) load_adds(strip + 2, nxt);
         tc::tmem_ld_wait();
+        if (ncat) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+        }
         if (live) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
@@ -390,13 +459,19 @@ static AmpPlan amp_plan(int Cp, int K, int dil, int nsplit) {
   const size_t nch = (size_t)K * parts;
   const size_t limit = 227 * 1024 - 1024;
   AmpPlan pl;
-  pl.acc_stride = (Cp + 31) / 32 * 32;
+  // split operands, narrow tiles: W_hi | W_lo side by side along N (2 MMA groups per tap, not 3).
+  // Measured: C=40 (N 48 -> 96) k=11 0.98 -> 0.61 ms per launch, k=7 0.70 -> 0.52; C=80 (N 80 -> 160)
+  // got slower (k=11 0.41 -> 0.53 ms: an N=160 MMA costs twice an N=80 one and the ring needs 20
+  // small weight copies per tap), so the concatenation is used up to N = 128 only.
+  pl.ncat = (nsplit == 3 && 2 * Cp <= 128) ? 1 : 0;
+  const size_t wslot = pl.ncat ? 2 * wb : wb;   // one ring slot (ncat: both parts of a tap)
+  pl.acc_stride = ((pl.ncat ? 2 * Cp : Cp) + 31) / 32 * 32;
   pl.ncols = (int)tc_cols_host(2 * pl.acc_stride);
   // Measured (r01): resident weights + 2 A buffers (one CTA per SM) beat streaming weights with two
   // CTAs per SM on the C=40/80 stages (33.0 vs 37.1 ms per step), so residency is preferred.
   if (2 * a_buf + nch * wb + 128 <= limit) { pl.resident = 1; pl.nabuf = 2; pl.smem = 2 * a_buf + nch * wb + 128; }
-  else if (2 * a_buf + 2 * wb + 128 <= limit) { pl.resident = 0; pl.nabuf = 2; pl.smem = 2 * a_buf + 2 * wb + 128; }
-  else { pl.resident = 0; pl.nabuf = 1; pl.smem = a_buf + 2 * wb + 128; }
+  else if (2 * a_buf + 2 * wslot + 128 <= limit) { pl.resident = 0; pl.nabuf = 2; pl.smem = 2 * a_buf + 2 * wslot + 128; }
+  else { pl.resident = 0; pl.nabuf = 1; pl.smem = a_buf + 2 * wslot + 128; }
   return pl;
 }
 
@@ -435,7 +510,7 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
   snprintf(kname, sizeof(kname), "amp_conv_tc_%s_c%dk%d", p.nsplit == 3 ? "bf16x3" : "bf16", p.C, p.K);
   KernelScope ks(kname, s, 2.0 * macs,
                  (double)p.B * p.C * p.L * ((p.nsplit == 3 ? 4.0 : 2.0) + 4.0 * (p.res ? 2 : 1)));
-  amp_conv_tc_kernel<<<grid, 320, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols);
+  amp_conv_tc_kernel<<<grid, 320, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols, pl.ncat);
   SVCB_LAUNCH_CHECK("amp_conv_tc");
   return SVCB_OK;
 }
