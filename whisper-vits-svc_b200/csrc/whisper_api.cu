@@ -12,7 +12,8 @@
 
 namespace svcb {
 int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
-                   int M, int N, int K, int epi, cudaStream_t s);
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0);
+int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s);
 int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
                              cudaStream_t s);
 int launch_rowmajor_to_image(const void* src, void* dst, int R, int K, int rows, cudaStream_t s);
@@ -27,7 +28,7 @@ struct WBlock {
 struct svcb_whisper {
   svcb_whisper_config cfg;
   std::map<std::string, std::pair<const float*, uint64_t>> tensors;
-  const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *pos, *lnp_g, *lnp_b;
+  const float *conv1_w, *conv1_b, *conv2_wimg, *conv2_b, *pos, *lnp_g, *lnp_b;
   std::vector<svcb::WBlock> blocks;
 };
 
@@ -94,7 +95,7 @@ int svcb_whisper_create(const void* dev_blob, size_t blob_bytes, const svcb_tens
   };
   const uint64_t D = c.n_state;
   w->conv1_w = get("conv1.w", (uint64_t)c.n_mels * 3 * D); w->conv1_b = get("conv1.b", D);
-  w->conv2_w = get("conv2.w", D * 3 * D); w->conv2_b = get("conv2.b", D);
+  w->conv2_wimg = get("conv2.wimg", D * 3 * D / 2); w->conv2_b = get("conv2.b", D);
   w->pos = get("pos", (uint64_t)c.n_ctx * D);
   w->lnp_g = get("ln_post.g", D); w->lnp_b = get("ln_post.b", D);
   w->blocks.resize(c.n_layer);
@@ -141,15 +142,11 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
     p.B = B; p.Cin = c.n_mels; p.Cout = D; p.Tin = n; p.K = 3; p.pad = 1; p.nq = n; p.act = ACT_GELU;
     SVCB_TRY(launch_conv1d(p, s));
   }
-  {  // conv2 stride 2 + GELU, permute to time-major, + positional embedding (:150-157)
-    ConvParams p;
-    p.x = h1; p.sxb = (long long)D * n; p.sxc = n; p.sxt = 1;
-    p.w = w->conv2_w; p.cout_pad = D; p.bias = w->conv2_b;
-    p.y = x; p.syb = (long long)n2 * D; p.syc = 1; p.syt = D;
-    p.B = B; p.Cin = D; p.Cout = D; p.Tin = n; p.K = 3; p.stride = 2; p.pad = 1; p.nq = n2; p.act = ACT_GELU;
-    p.addvec = w->pos;
-    SVCB_TRY(launch_conv1d(p, s));
-  }
+  // conv2 (k=3, stride 2) + GELU + positional embedding, time-major (:150-157) as a tensor-core GEMM:
+  // im2col tile image of h1 (parked in the MLP hidden buffer, free until the first block) x the
+  // [D, 3D] weight image; the fp32 CUDA-core version of this layer was 25 % of the encoder's time
+  SVCB_TRY(launch_im2col_s2_image(h1, mid, B, D, n, n2, s));
+  SVCB_TRY(launch_gemm_tc(mid, w->conv2_wimg, w->conv2_b, x, w->pos, M, D, 3 * D, 3, s, n2));
   for (int i = 0; i < c.n_layer; ++i) {
     const WBlock& b = w->blocks[i];
     SVCB_TRY(launch_ln_rows(x, b.ln1g, b.ln1b, a, M, D, true, s));

@@ -23,7 +23,9 @@
 
 namespace svcb {
 
-enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2 };
+// 3: fp32 out = GELU(acc + bias) + res[m % res_mod] — the stem's second convolution as a GEMM over an
+// im2col image, with the positional embedding (period n_ctx rows) as the addend (whisper/model.py:150-157)
+enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3 };
 
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 
@@ -35,7 +37,7 @@ __host__ __device__ inline size_t img_off(int m, int k, int KT) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __restrict__ Wimg,
-               const float* __restrict__ bias, void* out, const float* res, int M, int N, int K) {
+               const float* __restrict__ bias, void* out, const float* res, int M, int N, int K, int res_mod) {
   constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, ST_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], t_full[2], t_empty[2];
@@ -115,8 +117,9 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
         uint32_t v[16];
         tc::tmem_ld16(tbase + (uint32_t)c0, v);
         float r16[16];
-        if (EPI == EPI_RESID_F32 && m < M) {
-          const float4* rr = reinterpret_cast<const float4*>(res + (size_t)m * N + n0 + c0);
+        if ((EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) && m < M) {
+          const int mr = (EPI == EPI_GELU_ADD_F32 && res_mod > 0) ? m % res_mod : m;
+          const float4* rr = reinterpret_cast<const float4*>(res + (size_t)mr * N + n0 + c0);
 #pragma unroll
           for (int j = 0; j < 4; ++j) { const float4 q = rr[j]; r16[4 * j] = q.x; r16[4 * j + 1] = q.y; r16[4 * j + 2] = q.z; r16[4 * j + 3] = q.w; }
         }
@@ -125,7 +128,11 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-          if (EPI == EPI_RESID_F32) {
+          if (EPI == EPI_GELU_ADD_F32) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
+          }
+          if (EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) {
             float* o = static_cast<float*>(out) + (size_t)m * N + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -161,7 +168,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
 
 template <int BN, int EPI>
 static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, void* out,
-                         const float* res, int M, int N, int K, cudaStream_t s) {
+                         const float* res, int M, int N, int K, int res_mod, cudaStream_t s) {
   constexpr size_t smem = (size_t)GM_STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2);
   static bool attr = false;
   static int n_sm = 0;
@@ -175,26 +182,71 @@ static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
   const int ntiles = ((M + GM_BM - 1) / GM_BM) * (N / BN);
   const int grid = std::min(ntiles, n_sm);
   KernelScope ks("whisper_gemm_tc", s, 2.0 * M * (double)N * K,
-                 2.0 * ((double)M * K + (double)N * K) + (EPI == EPI_RESID_F32 ? 8.0 : 2.0) * M * (double)N);
-  gemm_tc_kernel<BN, EPI><<<grid, 320, smem, s>>>(A, W, bias, out, res, M, N, K);
+                 2.0 * ((double)M * K + (double)N * K) + (EPI == EPI_RESID_F32 ? 8.0 : EPI == EPI_GELU_ADD_F32 ? 4.0 : 2.0) * M * (double)N);
+  gemm_tc_kernel<BN, EPI><<<grid, 320, smem, s>>>(A, W, bias, out, res, M, N, K, res_mod);
   SVCB_LAUNCH_CHECK("gemm_tc");
   return SVCB_OK;
 }
 
 // A_img: tile image [ceil(M/128)][K/64][8][128][8]; W_img: tile image [N/256][K/64][8][256][8]
 int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, const float* res,
-                   int M, int N, int K, int epi, cudaStream_t s) {
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod) {
   if (M <= 0) return SVCB_OK;
   if (K % 64 || N % 256) { set_error("gemm_tc: need K % 64 == 0 and N % 256 == 0"); return SVCB_E_BAD_SHAPE; }
   const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(A_img);
   const __nv_bfloat16* W = static_cast<const __nv_bfloat16*>(W_img);
   switch (epi) {
-    case EPI_BF16_ROWMAJOR: return launch_gemm_t<256, EPI_BF16_ROWMAJOR>(A, W, bias, out, res, M, N, K, s);
-    case EPI_GELU_BF16_IMAGE: return launch_gemm_t<256, EPI_GELU_BF16_IMAGE>(A, W, bias, out, res, M, N, K, s);
-    case EPI_RESID_F32: return launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, s);
+    case EPI_BF16_ROWMAJOR: return launch_gemm_t<256, EPI_BF16_ROWMAJOR>(A, W, bias, out, res, M, N, K, 0, s);
+    case EPI_GELU_BF16_IMAGE: return launch_gemm_t<256, EPI_GELU_BF16_IMAGE>(A, W, bias, out, res, M, N, K, 0, s);
+    case EPI_RESID_F32: return launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, 0, s);
+    case EPI_GELU_ADD_F32:
+      if (!res) { set_error("gemm_tc: epilogue 3 needs the addend"); return SVCB_E_BAD_SHAPE; }
+      return launch_gemm_t<256, EPI_GELU_ADD_F32>(A, W, bias, out, res, M, N, K, res_mod, s);
   }
   set_error("gemm_tc: unknown epilogue");
   return SVCB_E_BAD_SHAPE;
+}
+
+// Stem conv2 (Conv1d(D, D, k=3, stride 2, pad 1), whisper/model.py:150) as a GEMM: this kernel builds
+// the A tile image of its im2col matrix, A[m = b*n2 + t2][k = j*D + ci] = h1[b][ci][2*t2 + j - 1]
+// (zero outside the sequence and in the rows that pad M to whole 128-row tiles), bf16.
+// One CTA = one (row tile, k tile): a k tile of 64 lies inside one tap j because D % 64 == 0.
+__global__ void __launch_bounds__(256)
+im2col_s2_image_kernel(const float* __restrict__ h1, __nv_bfloat16* __restrict__ img, int D, int n, int n2, int M) {
+  __shared__ float tile[64][129];
+  const int mt = blockIdx.x, kt = blockIdx.y, tid = threadIdx.x;
+  const int j = (kt * 64) / D, ci0 = (kt * 64) % D;
+  for (int idx = tid; idx < 64 * 128; idx += 256) {
+    const int cc = idx >> 7, r = idx & 127;
+    const int m = mt * 128 + r;
+    float v = 0.f;
+    if (m < M) {
+      const int b = m / n2, t2 = m - b * n2;
+      const int t = 2 * t2 + j - 1;
+      if (t >= 0 && t < n) v = __ldg(h1 + ((size_t)b * D + ci0 + cc) * n + t);
+    }
+    tile[cc][r] = v;
+  }
+  __syncthreads();
+  const int KT = 3 * D / 64;
+  __nv_bfloat16* dst = img + ((size_t)mt * KT + kt) * (GM_BM * GM_BK);
+  for (int idx = tid; idx < 8 * 128; idx += 256) {
+    const int kc = idx >> 7, r = idx & 127;
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(tile[kc * 8 + e][r]);
+    *reinterpret_cast<uint4*>(dst + (size_t)(kc * 128 + r) * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s) {
+  if (D % 64) { set_error("im2col_s2_image: D must be a multiple of 64"); return SVCB_E_BAD_SHAPE; }
+  const int M = B * n2;
+  dim3 grid((M + 127) / 128, 3 * D / 64);
+  KernelScope ks("im2col_s2_image", s, 0.0, (double)M * 3 * D * 2 + 4.0 * B * D * (double)n);
+  im2col_s2_image_kernel<<<grid, 256, 0, s>>>(h1, static_cast<__nv_bfloat16*>(img), D, n, n2, M);
+  SVCB_LAUNCH_CHECK("im2col_s2_image");
+  return SVCB_OK;
 }
 
 // row-major bf16 [R,K] -> tile image with `rows` rows per tile (128 for A, 256 for W); used by the

@@ -69,7 +69,8 @@ def pack_whisper(ckpt: dict):
 
     put("conv1.w", pack.pack_conv(sd["encoder.conv1.weight"].float()))
     put("conv1.b", sd["encoder.conv1.bias"])
-    put("conv2.w", pack.pack_conv(sd["encoder.conv2.weight"].float()))
+    # conv2 (k=3, stride 2) runs as a GEMM over an im2col image: W2[co][j*D + ci] = w[co][ci][j]
+    items.append(("conv2.wimg", _bf16_as_f32(sd["encoder.conv2.weight"].float().permute(0, 2, 1).reshape(D, 3 * D))))
     put("conv2.b", sd["encoder.conv2.bias"])
     pos = sd.get("encoder.positional_embedding")
     if pos is None:  # a buffer; absent from synthetic checkpoints, recomputed like the constructor does
