@@ -34,15 +34,6 @@ constexpr int P8_PAD = 32;
 __host__ __device__ inline int p8_rows_of(int L) { return P8_PAD + (L + 127) / 128 * 128 + P8_PAD; }
 int p8_rows(int L) { return p8_rows_of(L); }
 
-__device__ __forceinline__ float fast_sin(float x) {
-  // Cody-Waite reduction to [-pi, pi] then the SFU sine: abs error < 1e-6 for |x| < 1e3, an order
-  // of magnitude below the bf16x3 operand rounding already accepted here.
-  const float k = rintf(x * 0.15915494309189535f);
-  x = fmaf(k, -6.2831854820251465f, x);
-  x = fmaf(k, 1.7484555e-7f, x);
-  return __sinf(x);
-}
-
 // ------------------------------------------------------------------------------------ snake_pack
 // Register-resident (same scheme as amp_block_fused's ab_snake_run; the earlier version staged x and
 // the 2x-rate Snake values of an 8 x 506 tile in shared memory across three CTA barriers and was
@@ -186,8 +177,9 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 // across tiles through mbarriers:
 //   producer thread  A image rows of tile i+1 (bulk copies, 1-2 buffers) and the weight tiles
 //                    (all taps resident in shared memory when they fit, else a 2-slot ring per tile)
-//   MMA thread       all taps x split parts of tile i into TMEM accumulator (i & 1)
-//   4 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
+//   MMA warp         all taps x split parts of tile i into TMEM accumulator (i & 1); one elected lane
+//                    issues (tc::elect_one) inside warp-uniform control flow
+//   8 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
 struct AmpPlan { int resident, nabuf, acc_stride, ncols, ncat; size_t smem; };
 
 __global__ void __launch_bounds__(320, 1)
