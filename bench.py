@@ -359,7 +359,6 @@ def run_ours(args, hp, sd):
 
 def run_whisper(args):
     """BASELINE configs[2]: truncated Whisper large-v2 encoder (24 blocks), 16 x 30 s log-mel per step."""
-    from oracle import whisper_oracle as W
     from whisper_vits_svc_b200 import _lib, synth, whisper_infer
     assert torch.cuda.is_available()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))

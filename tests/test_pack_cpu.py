@@ -69,3 +69,24 @@ def test_packed_model_tensor_inventory(hp, sd):
     assert all(off % 256 == 0 for _, off, _ in table)
     name, off, n = table[5]
     assert torch.equal(blob[off // 4: off // 4 + n], items[name].reshape(-1))
+
+
+def test_whisper_conv2_weight_image_layout():
+    """The stem's stride-2 conv runs as a GEMM over an im2col image (csrc/whisper_gemm.cu:
+    im2col_s2_image): its weight must reach the kernel as W2[co][j*D + ci] = w[co][ci][j] in the bf16
+    GEMM tile image [N/256][K/64][8][256][8]."""
+    from whisper_vits_svc_b200 import synth, whisper_infer
+    dims = dict(synth.WHISPER_LARGE_V2_DIMS, n_audio_state=256, n_audio_head=4, n_audio_layer=4)
+    ck = synth.whisper_checkpoint(dims, seed=3)
+    items, cfg = whisper_infer.pack_whisper(ck)
+    named = dict(items)
+    assert "conv2.w" not in named and "conv2.wimg" in named
+    D = 256
+    img = named["conv2.wimg"].view(torch.bfloat16).view(D // 256, 3 * D // 64, 8, 256, 8).float()
+    w = ck["model_state_dict"]["encoder.conv2.weight"].float().bfloat16().float()  # [co, ci, j]
+    g = torch.Generator().manual_seed(0)
+    for _ in range(200):
+        co = int(torch.randint(0, D, (1,), generator=g)); ci = int(torch.randint(0, D, (1,), generator=g))
+        j = int(torch.randint(0, 3, (1,), generator=g))
+        k = j * D + ci
+        assert float(img[co // 256, k // 64, (k % 64) // 8, co % 256, k % 8]) == float(w[co, ci, j])
