@@ -90,3 +90,27 @@ def test_whisper_conv2_weight_image_layout():
         j = int(torch.randint(0, 3, (1,), generator=g))
         k = j * D + ci
         assert float(img[co // 256, k // 64, (k % 64) // 8, co % 256, k % 8]) == float(w[co, ci, j])
+
+
+def test_stem_conv2_im2col_equivalence():
+    """The identity the device path relies on (csrc/whisper_gemm.cu:im2col_s2_image + epilogue 3):
+    Conv1d(D, D, k=3, stride=2, padding=1)(h)[b, :, t2] == A[b*n2 + t2, :] @ W2^T with
+    A[m, j*D + ci] = h[b, ci, 2*t2 + j - 1] (zero outside) and W2[co, j*D + ci] = w[co, ci, j]."""
+    g = torch.Generator().manual_seed(4)
+    B, D, n = 2, 16, 37
+    h = torch.randn(B, D, n, generator=g)
+    w = torch.randn(D, D, 3, generator=g)
+    bias = torch.randn(D, generator=g)
+    ref = F.conv1d(h, w, bias, stride=2, padding=1)            # [B, D, n2]
+    n2 = (n - 1) // 2 + 1
+    assert ref.shape[-1] == n2
+    A = torch.zeros(B * n2, 3 * D)
+    for b in range(B):
+        for t2 in range(n2):
+            for j in range(3):
+                t = 2 * t2 + j - 1
+                if 0 <= t < n:
+                    A[b * n2 + t2, j * D:(j + 1) * D] = h[b, :, t]
+    W2 = w.permute(0, 2, 1).reshape(D, 3 * D)
+    got = (A @ W2.t() + bias).view(B, n2, D).permute(0, 2, 1)
+    assert torch.allclose(got, ref, atol=1e-4)
