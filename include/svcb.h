@@ -103,6 +103,11 @@ void svcb_model_destroy(svcb_model* m);
 /* Bytes of caller-owned scratch needed by any of the calls below at (B, T frames). */
 size_t svcb_workspace_bytes(const svcb_model* m, int32_t B, int32_t T);
 
+/* Bytes of scratch svcb_source needs at (B, T): only the per-frame phase scan (3*B*n_harm*T doubles),
+ * not the whole pipeline's peak — pitch2source runs on the WHOLE utterance before the 2500-frame
+ * chunk loop (svc_inference.py:89-91), so its scratch must stay O(T) small for hour-long inputs. */
+size_t svcb_source_workspace_bytes(const svcb_model* m, int32_t B, int32_t T);
+
 /* Replaces: Generator.pitch2source (vits_decoder/generator.py:160-165) ->
  * SourceModuleHnNSF.forward (nsf.py:383-394) -> SineGen (nsf.py:217-316).
  * f0 [B,T] Hz (0 = unvoiced); rand_ini [B,n_harm] replaces torch.rand (nsf.py:232-235; column 0

@@ -5,6 +5,11 @@ The reference's internal RNG calls are answered with the seeded tensors of tests
 (in the order the reference draws them: torch.rand -> rand_ini, torch.randn_like -> noise, then
 torch.randn_like -> eps), so the fixtures pin the reference's arithmetic, not its RNG stream.
 Also asserts that oracle/svc_oracle.py reproduces every fixture.
+
+`whisper_case` does the same for the PPG extractor: the reference's `Whisper` module is built from a
+synthetic checkpoint through the loader surgery of whisper/inference.py:11-20 (decoder deleted, last
+quarter of the encoder blocks deleted, strict=False load) and `model.encoder(mel)` is stored next to
+the mel; oracle/whisper_oracle.py must reproduce it.
 """
 import os
 import sys
@@ -92,6 +97,50 @@ def gen_case(name, hp, seed, B, T):
     print(name, "wave peak %.3f" % wave.abs().max().item(), "oracle-vs-reference max abs", err)
 
 
+WHISPER_CASES = {
+    # name: (dims overrides, checkpoint seed, B, n_frames, input seed)
+    "whisper_d256_l8_b2_n200": (dict(n_audio_state=256, n_audio_head=4, n_audio_layer=8), 21, 2, 200, 31),
+    "whisper_d512_l4_b1_n301": (dict(n_audio_state=512, n_audio_head=8, n_audio_layer=4), 22, 1, 301, 32),
+}
+_SMALL_TEXT = dict(n_vocab=64, n_text_ctx=8, n_text_state=64, n_text_head=1, n_text_layer=1)
+
+
+def whisper_dims(over):
+    return dict(synth.WHISPER_LARGE_V2_DIMS, **_SMALL_TEXT, **over)
+
+
+def whisper_mel(seed, B, n):
+    """SURVEY.md §8d config 3 input recipe: N(0,1) clipped to the log-mel range [-1, 1.5]."""
+    return torch.randn(B, 80, n, generator=torch.Generator().manual_seed(seed)).clamp(-1, 1.5)
+
+
+def ref_whisper(ck):
+    """whisper/inference.py:11-20 verbatim in effect (the checkpoint is passed in, not read from disk)."""
+    wm = ref_import.import_whisper_model()
+    model = wm.Whisper(wm.ModelDimensions(**ck["dims"]))
+    del model.decoder
+    cut = len(model.encoder.blocks) // 4
+    cut = -1 * cut
+    del model.encoder.blocks[cut:]
+    model.load_state_dict(ck["model_state_dict"], strict=False)
+    model.eval()
+    return model
+
+
+def whisper_case(name):
+    from oracle import whisper_oracle as WO
+    over, ck_seed, B, n, in_seed = WHISPER_CASES[name]
+    ck = synth.whisper_checkpoint(whisper_dims(over), seed=ck_seed)
+    mel = whisper_mel(in_seed, B, n)
+    with torch.no_grad():
+        ppg = ref_whisper(ck).encoder(mel)
+    ppg_o = WO.audio_encoder(ck, mel)
+    err = (ppg - ppg_o).abs().max().item()
+    assert err < 1e-5, f"whisper oracle != reference ({err})"
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), mel=mel.numpy(), ppg=ppg.numpy())
+    print(name, "ppg rms %.3f" % ppg.pow(2).mean().sqrt().item(), "oracle-vs-reference max abs", err)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     hp = hparams.load_hparams(os.path.join(ROOT, "configs", "base.yaml"))
@@ -100,3 +149,5 @@ if __name__ == "__main__":
     hp24 = hparams.override(hp, gen__upsample_input=80, data__sampling_rate=24000)
     gen_case("gen80_b2_t36", hp24, seed=13, B=2, T=36)
     gen_case("gen192_b1_t64", hp, seed=14, B=1, T=64)
+    for name in WHISPER_CASES:
+        whisper_case(name)

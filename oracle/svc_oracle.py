@@ -14,8 +14,8 @@ Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline /
 Parity status: the reference ships no tests or golden vectors,
 so the pin is the reference code itself: `oracle/make_golden.py` imports
 `/root/reference` in the build container, checks this restatement against it
-(tests/test_oracle_vs_reference.py does the same when the reference is
-present) and writes `tests/golden/*.npz`, which travel to the GPU box.
+(tests/test_oracle_cpu.py::test_oracle_matches_reference_live does the same when the
+reference is present) and writes `tests/golden/*.npz`, which travel to the GPU box.
 
 Reference citations are relative to /root/reference.
 """

@@ -3,8 +3,12 @@ truncated Whisper AudioEncoder the reference runs (whisper/model.py:132-163 with
 surgery, whisper/inference.py:11-29: decoder deleted, last quarter of the encoder blocks deleted,
 ln_post kept).  Consumes the reference checkpoint format {"dims", "model_state_dict"}.
 
-Parity status: pinned by importing the reference (tests/test_oracle_cpu.py, oracle/make_golden.py);
-the reference ships no golden vectors for this path."""
+Parity status: the reference ships no golden vectors for this path, so the pin is the reference code
+itself: `oracle/make_golden.py:whisper_case` builds the unmodified `whisper.model.Whisper` through the
+loader surgery, checks this restatement against `model.encoder(mel)` (max-abs 0.0) and writes
+`tests/golden/whisper_*.npz`; `tests/test_oracle_cpu.py::test_whisper_oracle_matches_golden` re-checks the
+fixtures everywhere and `::test_whisper_oracle_matches_reference_live` repeats the live comparison where
+/root/reference exists."""
 from __future__ import annotations
 
 import math

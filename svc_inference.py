@@ -30,6 +30,8 @@ def main(args):
     if args.vec is None or args.pit is None:
         raise SystemExit("--vec and --pit are required: the HuBERT / CREPE extractors are out of scope of this build "
                          "(use the reference's hubert/inference.py and pitch/inference.py to produce them)")
+    if not torch.cuda.is_available():
+        raise SystemExit("this build has no CPU path: a CUDA (sm_100a) device is required")
     if args.ppg is None:
         from whisper_vits_svc_b200 import whisper_infer
         args.ppg = "svc_tmp.ppg.npy"
@@ -37,8 +39,6 @@ def main(args):
         wm = whisper_infer.load_model(os.path.join("whisper_pretrain", "large-v2.pt"), "cuda")
         whisper_infer.pred_ppg(wm, args.wave, args.ppg, "cuda")
     logging.basicConfig(level=logging.DEBUG if args.debug else logging.INFO)
-    if not torch.cuda.is_available():
-        raise SystemExit("this build has no CPU path: a CUDA (sm_100a) device is required")
     device = torch.device("cuda")
     hp = hparams.load_hparams(args.config)
     model = models.SynthesizerInfer(hp.data.filter_length // 2 + 1, hp.data.segment_size // hp.data.hop_length, hp)

@@ -118,3 +118,45 @@ def test_product_mel_filters_match_oracle():
     from oracle import whisper_oracle as wo
     from whisper_vits_svc_b200 import whisper_infer
     assert np.array_equal(whisper_infer.mel_filters().numpy(), wo.slaney_mel_filterbank())
+
+
+# ------------------------------------------------------------------ PPG extractor oracle (whisper/model.py:144-163)
+WHISPER_GOLDEN = ["whisper_d256_l8_b2_n200", "whisper_d512_l4_b1_n301"]
+
+
+def _whisper_case(name):
+    from oracle import make_golden as mg
+    over, ck_seed, B, n, in_seed = mg.WHISPER_CASES[name]
+    return synth.whisper_checkpoint(mg.whisper_dims(over), seed=ck_seed), mg.whisper_mel(in_seed, B, n)
+
+
+@pytest.mark.parametrize("name", WHISPER_GOLDEN)
+def test_whisper_oracle_matches_golden(name):
+    """tests/golden/whisper_*.npz are outputs of the unmodified reference `Whisper.encoder` after the
+    loader surgery (oracle/make_golden.py:whisper_case); the restatement must reproduce them."""
+    from oracle import whisper_oracle as wo
+    g = _load(name)
+    ck, mel = _whisper_case(name)
+    assert np.array_equal(mel.numpy(), g["mel"])          # the input recipe is reproducible
+    got = wo.audio_encoder(ck, mel)
+    assert got.shape == g["ppg"].shape
+    assert max_abs(got, g["ppg"]) <= 1e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("over,B,n", [(dict(n_audio_state=256, n_audio_head=4, n_audio_layer=8), 2, 120),
+                                      (dict(n_audio_state=384, n_audio_head=6, n_audio_layer=4), 1, 77)])
+def test_whisper_oracle_matches_reference_live(over, B, n):
+    """The pin itself: reference `Whisper(dims)` -> `del decoder`, `del encoder.blocks[-(n//4):]`,
+    `load_state_dict(strict=False)` exactly as whisper/inference.py:11-20, then `model.encoder(mel)`
+    against `whisper_oracle.audio_encoder` on the same checkpoint and mel."""
+    from oracle import make_golden as mg, whisper_oracle as wo
+    ck = synth.whisper_checkpoint(mg.whisper_dims(over), seed=5)
+    mel = mg.whisper_mel(6, B, n)
+    model = mg.ref_whisper(ck)
+    assert len(model.encoder.blocks) == wo.kept_layers(ck["dims"])
+    with torch.no_grad():
+        ref = model.encoder(mel)
+    got = wo.audio_encoder(ck, mel)
+    assert got.shape == ref.shape == (B, (n - 1) // 2 + 1, over["n_audio_state"])
+    assert max_abs(got, ref) <= 1e-6

@@ -40,6 +40,9 @@ def test_golden_full(model, hp, name):
     d = make_inputs(int(g["seed"]), int(g["B"]), int(g["T"]), hp, ragged=bool(g["ragged"]))
     src = model.pitch2source(d["pit"], rand_ini=d["rand_ini"], noise=d["noise"])
     assert max_abs(src, g["source"]) <= 1e-5
+    # integer work is bit-exact on identical input: the GOLDEN source through source2wav == the reference's pcm
+    assert np.array_equal(model.source2wav(torch.from_numpy(g["source"][:1])), g["pcm"])
+    # (the device's own source differs from the golden one by <= 1e-5, i.e. at most one int16 step)
     assert np.abs(model.source2wav(src[:1]).astype(np.int32) - g["pcm"].astype(np.int32)).max() <= 1
     wave = model.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], torch.from_numpy(g["source"]),
                            eps=d["eps"])
@@ -247,3 +250,34 @@ def test_tiny_lengths_tensor_core_mode(model_tc, hp, sd, B, T):
     err = max_abs(wave, wave_o)
     print(f"B={B} T={T} (precision 3): wave max-abs err {err:.3e}")
     assert err <= 2e-4
+
+
+def test_large_snake_alpha_tensor_core_mode(hp, sd):
+    """Trained BigVGAN checkpoints reach e^alpha ~ 10-50 (arguments of sin in the hundreds), far outside
+    the synthetic N(0, 0.4^2) log-alphas: Snake's sin must stay accurate there (csrc/common.cuh:snake_sin
+    reduces to [-pi, pi] before the hardware approximation).  alpha ~ U(-1, 3.5) (e^alpha up to 33) and
+    beta ~ U(-1.5, 0.5) (gain 1/e^beta up to 4.5) in every SnakeAlias of the generator — the narrow stages
+    (amp_block_fused), the wide ones (snake_pack + amp_conv_tc) and activation_post — against the oracle."""
+    from whisper_vits_svc_b200 import models
+    g = torch.Generator().manual_seed(404)
+    sd2 = dict(sd)
+    for k in sd:
+        if k.startswith("dec.") and k.endswith(".act.alpha"):
+            sd2[k] = torch.rand(sd[k].shape, generator=g) * 4.5 - 1.0
+        elif k.startswith("dec.") and k.endswith(".act.beta"):
+            sd2[k] = torch.rand(sd[k].shape, generator=g) * 2.0 - 1.5
+    m = models.SynthesizerInfer(513, 25, hp, precision=3)
+    m.load_state_dict(sd2)
+    m.to("cuda")
+    d = make_inputs(52, 2, 40, hp, ragged=True)
+    src = O.pitch2source(sd2, hp, d["pit"], d["rand_ini"], d["noise"])
+    st = {}
+    wave_o = O.synthesizer_infer(sd2, hp, d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, d["eps"], stages=st)
+    names = [f"gen_stage{i}" for i in range(5)]
+    taps = {k: torch.zeros(tuple(st[k].shape), device="cuda") for k in names}
+    wave = m.inference(d["ppg"], d["vec"], d["pit"], d["spk"], d["ppg_l"], src, eps=d["eps"], taps=taps)
+    for k in names:
+        print(f"large alpha {k}: max-abs {max_abs(taps[k], st[k]):.3e} (peak {float(st[k].abs().max()):.2f})")
+    err = max_abs(wave, wave_o)
+    print(f"large alpha: wave max-abs {err:.3e}")
+    assert err <= WAVE_TOL

@@ -93,6 +93,52 @@ def test_encoder_vs_oracle(state, heads, layers, B, n):
     assert r <= 2e-2 and cos >= 0.999
 
 
+@pytest.mark.parametrize("name", ["whisper_d256_l8_b2_n200", "whisper_d512_l4_b1_n301"])
+def test_encoder_vs_reference_golden(name):
+    """tests/golden/whisper_*.npz = `Whisper.encoder(mel)` of the UNMODIFIED reference after the loader
+    surgery (oracle/make_golden.py:whisper_case, fp32 CPU).  The device encoder (bf16 operands, fp32
+    accumulate) against it, same relative gate as against the oracle."""
+    import os
+    from oracle import make_golden as mg
+    from tests.util import GOLDEN
+    from whisper_vits_svc_b200 import whisper_infer
+    over, ck_seed, B, n, in_seed = mg.WHISPER_CASES[name]
+    ck = synth.whisper_checkpoint(mg.whisper_dims(over), seed=ck_seed)
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    got = whisper_infer.WhisperB200(ck, "cuda").encoder(torch.from_numpy(g["mel"])).cpu()
+    ref = torch.from_numpy(g["ppg"])
+    assert got.shape == ref.shape
+    r = rel_l2(got, ref)
+    cos = float(F.cosine_similarity(got.flatten(), ref.flatten(), dim=0))
+    print(f"{name}: rel-l2 {r:.3e}, cosine {cos:.6f}, max-abs {max_abs(got, ref):.3e}")
+    assert r <= 2e-2 and cos >= 0.999
+
+
+def test_encoder_full_size_vs_oracle():
+    """BASELINE config #3 geometry: large-v2 dims (D=1280, 20 heads, 32 layers -> 24 kept), 30 s items
+    (n=3000 frames -> all 1500 positions), B=2 so the M dimension spans many 128-row tiles and an item
+    boundary.  bf16 rounding accumulates through 24 residual blocks; the gate stays rel-L2 <= 2e-2 and
+    cosine >= 0.999 against the fp32 oracle (the reference itself runs fp16 on GPU)."""
+    from whisper_vits_svc_b200 import whisper_infer
+    ck = synth.whisper_checkpoint(seed=77)
+    assert W.kept_layers(ck["dims"]) == 24
+    mel = torch.randn(2, 80, 3000, generator=torch.Generator().manual_seed(9)).clamp(-1, 1.5)
+    enc = whisper_infer.WhisperB200(ck, "cuda").encoder
+    got = enc(mel).cpu()
+    del enc
+    torch.cuda.empty_cache()
+    ref = W.audio_encoder(ck, mel[:1])        # one item on the host: ~1.7 TFLOP of fp32
+    assert got.shape == (2, 1500, 1280)
+    r = rel_l2(got[:1], ref)
+    cos = float(F.cosine_similarity(got[:1].flatten(), ref.flatten(), dim=0))
+    print(f"whisper large-v2 geometry, 24 layers, 30 s: rel-l2 {r:.3e}, cosine {cos:.6f}, max-abs {max_abs(got[:1], ref):.3e}")
+    assert torch.isfinite(got).all()
+    assert r <= 2e-2 and cos >= 0.999
+    # item independence at full size: the second item alone == in the batch
+    one = whisper_infer.WhisperB200(ck, "cuda").encoder(mel[1:2]).cpu()
+    assert max_abs(one, got[1:2]) <= 1e-5
+
+
 def _small_encoder():
     from whisper_vits_svc_b200 import whisper_infer
     dims = dict(synth.WHISPER_LARGE_V2_DIMS, n_audio_state=256, n_audio_head=4, n_audio_layer=4)

@@ -88,6 +88,7 @@ SIGNATURES = {
     "svcb_model_create": (c_int, [c_void_p, c_size_t, POINTER(TensorEntry), c_int32, POINTER(Config), POINTER(c_void_p)]),
     "svcb_model_destroy": (None, [c_void_p]),
     "svcb_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "svcb_source_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
     "svcb_source": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "svcb_source2wav": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
     "svcb_prior": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, POINTER(Taps), c_void_p]),

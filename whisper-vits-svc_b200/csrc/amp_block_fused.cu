@@ -81,7 +81,7 @@ __device__ __forceinline__ void ab_snake_run(const float* __restrict__ xr, float
       float uo = x[p + 3] * fu[10];
       uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
       uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
-      const float se = __sinf(ue * a_), so = __sinf(uo * a_);   // (the x2 gain is folded into fu: exact)
+      const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);   // (the x2 gain is folded into fu: exact)
       vv[2 * p] = fmaf(b_, se * se, ue);
       vv[2 * p + 1] = fmaf(b_, so * so, uo);
     }
@@ -108,7 +108,7 @@ __device__ __forceinline__ void ab_snake_run(const float* __restrict__ xr, float
           float u = 0.f;
           for (int d = q; d < q + 6; ++d) u = fmaf(xr[min(max(a - 3 + d, lo_i), hi_i)], f_up[11 + q - 2 * d], u);
           u *= 2.f;
-          const float sn = __sinf(u * a_);
+          const float sn = snake_sin(u * a_);
           acc = fmaf(fmaf(b_, sn * sn, u), f_dn[k], acc);
         }
       }
@@ -279,11 +279,8 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   if (TOUT < 64) { set_error("amp_block_fused: receptive field too large for the tile"); return SVCB_E_UNSUPPORTED; }
   const size_t smem = ((size_t)3 * C * WS + (size_t)C * p.K * AbCfg<C, V>::CP) * sizeof(float);
   if (smem > 227 * 1024 - 1024) { set_error("amp_block_fused: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_block_fused_kernel<C, K, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(amp_block_fused_kernel<C, K, V>, smem, attr_cache));
   dim3 grid((p.L + TOUT - 1) / TOUT, p.B);
   char kname[64];
   snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);

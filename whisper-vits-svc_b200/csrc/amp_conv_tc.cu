@@ -70,7 +70,7 @@ __device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, in
       float uo = x[p + 3] * fu[10];
       uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
       uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
-      const float se = __sinf(ue * a_), so = __sinf(uo * a_);   // fu carries UpSample1d's x2 gain
+      const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);   // fu carries UpSample1d's x2 gain
       vv[2 * p] = fmaf(b_, se * se, ue);
       vv[2 * p + 1] = fmaf(b_, so * so, uo);
     }
@@ -93,7 +93,7 @@ __device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, in
           float u = 0.f;
           for (int d = q; d < q + 6; ++d) u = fmaf(__ldg(xr + min(max(a - 3 + d, 0), L - 1)), f_up[11 + q - 2 * d], u);
           u *= 2.f;
-          const float sn = __sinf(u * a_);
+          const float sn = snake_sin(u * a_);
           acc = fmaf(fmaf(b_, sn * sn, u), f_dn[k], acc);
         }
       }
@@ -480,18 +480,10 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
   }
   const AmpPlan pl = amp_plan(p.Cp, p.K, p.dil, p.nsplit);
   if (pl.smem > 227 * 1024 - 512) { set_error("amp_conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
-  static size_t attr_bytes = 0;  // the dynamic limit excludes the kernel's (small) static shared memory
-  static int n_sm = 0;
-  if (pl.smem > attr_bytes) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(amp_conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)pl.smem));
-    attr_bytes = pl.smem;
-  }
-  if (!n_sm) {
-    int dev = 0;
-    SVCB_CUDA_CHECK(cudaGetDevice(&dev));
-    SVCB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  }
+  static DevSmemCache attr_cache;  // the dynamic limit excludes the kernel's (small) static shared memory
+  SVCB_CUDA_CHECK(ensure_dyn_smem(amp_conv_tc_kernel, pl.smem, attr_cache));
+  const int n_sm = device_sm_count();
+  if (n_sm <= 0) { set_error("amp_conv_tc: cannot query the SM count"); return SVCB_E_CUDA; }
   int occ = 1;
   SVCB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, amp_conv_tc_kernel, 320, pl.smem));
   occ = std::max(1, std::min(occ, 512 / pl.ncols));

@@ -15,6 +15,18 @@ static thread_local int64_t g_launches = 0;
 void set_error(const std::string& msg) { g_err = msg; }
 void count_launch() { ++g_launches; }
 
+int device_sm_count() {
+  static std::atomic<int> cache[kMaxDevices];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const bool cached = dev >= 0 && dev < kMaxDevices;
+  int n = cached ? cache[dev].load(std::memory_order_relaxed) : 0;
+  if (n > 0) return n;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  if (cached) cache[dev].store(n, std::memory_order_relaxed);
+  return n;
+}
+
 // ----------------------------------------------------------------------------- kernel timing
 struct TimedLaunch { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
 static bool g_timing = false;
@@ -799,6 +811,11 @@ size_t svcb_workspace_bytes(const svcb_model* m, int32_t B, int32_t T) {
   }
   peak = std::max(peak, source_scan_ws_bytes(B, T, m->cfg.n_harmonics) + 256);
   return peak + 4096;
+}
+
+size_t svcb_source_workspace_bytes(const svcb_model* m, int32_t B, int32_t T) {
+  if (!m || B <= 0 || T <= 0) return 0;
+  return source_scan_ws_bytes(B, T, m->cfg.n_harmonics) + 4096;
 }
 
 static int make_ctx(Ctx& ctx, void* ws, size_t ws_bytes, const svcb_taps* taps, svcb_stream stream) {

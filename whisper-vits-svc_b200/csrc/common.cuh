@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 #include "svcb.h"
@@ -39,11 +40,47 @@ struct KernelScope {
     }                                                                                    \
   } while (0)
 
+// Per-device caches: cudaFuncAttributeMaxDynamicSharedMemorySize and the SM count belong to a device
+// (context), not to the process — a handle re-packed on another GPU of the same process must set the
+// attribute again there.  Lock-free: a racing thread at worst repeats an idempotent call.
+constexpr int kMaxDevices = 64;
+struct DevSmemCache {
+  std::atomic<size_t> bytes[kMaxDevices];
+};
+template <typename Kern>
+inline cudaError_t ensure_dyn_smem(Kern kernel, size_t bytes, DevSmemCache& cache) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= kMaxDevices)
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  size_t seen = cache.bytes[dev].load(std::memory_order_relaxed);
+  if (bytes <= seen) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return e;
+  while (seen < bytes && !cache.bytes[dev].compare_exchange_weak(seen, bytes, std::memory_order_relaxed)) {
+  }
+  return cudaSuccess;
+}
+int device_sm_count();   // of the current device (cached per device); 0 on error
+
 #define SVCB_TRY(expr)            \
   do {                            \
     int _s = (expr);              \
     if (_s != SVCB_OK) return _s; \
   } while (0)
+
+// sin() for the Snake activations of the tensor-core / fused paths: two-constant Cody-Waite reduction
+// to [-pi, pi] followed by the hardware approximation.  `__sinf` alone multiplies by 1/2pi in fp32 first,
+// so its absolute error grows like |x| * 2^-24: trained BigVGAN log-alphas reach e^alpha ~ 10-50, i.e.
+// arguments in the hundreds (round-1 advice).  Reduced, the error stays at the MUFU level (~4e-7) for
+// |x| < 1e5; four extra FMA-pipe instructions per value.
+__device__ __forceinline__ float snake_sin(float x) {
+  const float k = (fmaf(x, 0.15915494309189535f, 12582912.f)) - 12582912.f;   // rint(x / 2pi), |x| < 2^22
+  float r = fmaf(k, -6.28125f, x);                   // 2pi = 6.28125 (exact in 8 bits) + 1.9353071795864769e-3
+  r = fmaf(k, -1.9353071795864769e-3f, r);
+  return __sinf(r);
+}
 
 // ----------------------------------------------------------------------------- conv1d
 enum ConvFlags : int {

@@ -171,12 +171,8 @@ static int pick_cog(int cout_pad) {
 template <int TPT>
 static int launch_t(const ConvParams& p, int cog, int ci_tile, int xspan, size_t smem,
                     cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(conv1d_kernel<TPT>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(conv1d_kernel<TPT>, 200 * 1024, attr_cache));
   dim3 block(32, cog);
   dim3 grid((p.nq + 32 * TPT - 1) / (32 * TPT), (p.cout_pad / 8 + cog - 1) / cog, p.B);
   const int cout_real = (p.flags & CONV_GATE) ? p.Cout / 2 : p.Cout;

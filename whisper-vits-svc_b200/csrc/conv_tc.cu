@@ -257,11 +257,8 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
   if (conv_tc_smem_bytes(p, 2) <= 113 * 1024 && tc_cols(p.bn) <= 256) wst = 2;
   const size_t smem = conv_tc_smem_bytes(p, wst);
   if (smem > 227 * 1024 - 512) { set_error("conv_tc: tile does not fit shared memory"); return SVCB_E_UNSUPPORTED; }
-  static size_t attr_bytes = 0;
-  if (smem > attr_bytes) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_bytes = smem;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(conv_tc_kernel, smem, attr_cache));
   dim3 grid((p.Tout + CT_M - 1) / CT_M, p.ntiles, p.B);
   const int cout_real = (p.flags & CONV_GATE) ? p.Cout / 2 : p.Cout;
   char kname[64];

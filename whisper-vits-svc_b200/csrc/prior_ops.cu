@@ -62,12 +62,8 @@ int launch_layernorm_c(const float* x, const float* r, const float* gamma, const
                        cudaStream_t s) {
   const size_t smem = ((size_t)C * 32 + 8 * 32) * sizeof(float);
   if (smem > 200 * 1024) { set_error("layernorm_c: C too large"); return SVCB_E_UNSUPPORTED; }
-  static bool attr = false;
-  if (!attr) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(layernorm_c_kernel,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(layernorm_c_kernel, 200 * 1024, attr_cache));
   dim3 grid((T + 31) / 32, B), block(32, 8);
   KernelScope ks("layernorm_c", s, 8.0 * B * C * (double)T, 4.0 * B * C * (double)T * (r ? 3 : 2));
   layernorm_c_kernel<<<grid, block, smem, s>>>(x, r, gamma, beta, y, C, T, gb_batch_stride, eps);
@@ -280,12 +276,8 @@ int launch_rel_attention(const float* qkv, const float* ek, const float* ev,
   const int nrel = 2 * window + 1;
   const size_t smem = (size_t)(RA_BQ * (D + 4) + RA_BK * (D + 4) + RA_BK * D + RA_BQ * (RA_BK + 4) +
                                2 * nrel * D + RA_BQ * nrel + 3 * RA_BQ) * sizeof(float);
-  static bool attr = false;
-  if (!attr) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(rel_attention_kernel<96>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(rel_attention_kernel<96>, 200 * 1024, attr_cache));
   dim3 grid((T + RA_BQ - 1) / RA_BQ, heads, B);
   KernelScope ks("rel_attention", s, 4.0 * B * H * (double)T * T, 16.0 * B * H * (double)T);
   rel_attention_kernel<96><<<grid, 256, smem, s>>>(qkv, ek, ev, lengths, out, H, heads, window, T);

@@ -170,15 +170,10 @@ template <int BN, int EPI>
 static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, void* out,
                          const float* res, int M, int N, int K, int res_mod, cudaStream_t s) {
   constexpr size_t smem = (size_t)GM_STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2);
-  static bool attr = false;
-  static int n_sm = 0;
-  if (!attr) {
-    SVCB_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0;
-    SVCB_CUDA_CHECK(cudaGetDevice(&dev));
-    SVCB_CUDA_CHECK(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-    attr = true;
-  }
+  static DevSmemCache attr_cache;
+  SVCB_CUDA_CHECK(ensure_dyn_smem(gemm_tc_kernel<BN, EPI>, smem, attr_cache));
+  const int n_sm = device_sm_count();
+  if (n_sm <= 0) { set_error("gemm_tc: cannot query the SM count"); return SVCB_E_CUDA; }
   const int ntiles = ((M + GM_BM - 1) / GM_BM) * (N / BN);
   const int grid = std::min(ntiles, n_sm);
   KernelScope ks("whisper_gemm_tc", s, 2.0 * M * (double)N * K,

@@ -94,8 +94,9 @@ def chunk_plan(all_frame: int, hop_size: int, out_chunk: int = 2500, hop_frame: 
 def svc_infer(model, spk, pit, ppg, vec, hp, device, write_pit_wav: str | None = "svc_out_pit.wav",
               rand_ini=None, noise=None, eps_fn=None, max_batch: int = 16):
     """svc_inference.py:77-134.  Returns the float32 waveform as a numpy array of length
-    n_frames*hop - 1 (the reference's last-chunk slice).  `rand_ini`/`noise`/`eps_fn(chunk_idx, B, C, T)`
-    inject the reference's random draws for parity tests."""
+    n_frames*hop - 1 (the reference's last-chunk slice).  `rand_ini`/`noise` and
+    `eps_fn(chunk_idx, 1, n_frames) -> [1, inter_channels, n_frames]` (one call per chunk) inject the
+    reference's random draws for parity tests."""
     len_min = min(pit.size(0), vec.size(0), ppg.size(0))
     pit, vec, ppg = pit[:len_min], vec[:len_min, :], ppg[:len_min, :]
     hop = int(hp.data.hop_length)

@@ -168,7 +168,9 @@ class SynthesizerInfer(torch.nn.Module):
         rand_ini, noise = self._f32(rand_ini), self._f32(noise)
         assert rand_ini.shape == (B, nh) and noise.shape == (B, L, nh)
         out = torch.empty(B, 1, L, device=dev, dtype=torch.float32)
-        ws = self._workspace(B, T)
+        # the source scan needs O(B*T) bytes, not the pipeline's peak: the host loop calls this on the
+        # whole utterance before chunking (svc_inference.py:89-91)
+        ws = torch.empty(int(_lib.load().svcb_source_workspace_bytes(self._handle, B, T)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             st = _lib.load().svcb_source(self._handle, f0.data_ptr(), rand_ini.data_ptr(), noise.data_ptr(),
                                          out.data_ptr(), B, T, ws.data_ptr(), ws.numel(), self._stream())

@@ -224,11 +224,15 @@ def mel_filters(n_mels: int = N_MELS, sr: int = SAMPLE_RATE, n_fft: int = N_FFT)
 
 def load_audio(path: str, sr: int = SAMPLE_RATE) -> np.ndarray:
     """whisper/audio.py:24-26 uses librosa.load(sr=16000) (mono float32, resampled); restated with
-    scipy: int PCM -> [-1,1), channel mean, polyphase resampling."""
+    scipy: int PCM -> [-1,1), channel mean, polyphase resampling.  Differences from the reference
+    extractor: .wav only (librosa/audioread decode more containers), and `resample_poly` instead of
+    librosa's soxr/kaiser resampler, so PPGs of non-16 kHz files differ slightly from the reference's."""
     from scipy.io import wavfile
     from scipy.signal import resample_poly
     rate, x = wavfile.read(path)
-    if x.dtype.kind in "iu":
+    if x.dtype == np.uint8:     # 8-bit WAV is unsigned with the zero level at 128
+        x = (x.astype(np.float32) - 128.0) / 128.0
+    elif x.dtype.kind in "iu":
         x = x.astype(np.float32) / float(np.iinfo(x.dtype).max + 1)
     x = x.astype(np.float32)
     if x.ndim > 1:
