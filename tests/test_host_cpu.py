@@ -133,3 +133,6 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in d["config"]
+    # the arm times a bounded sample of OUR headline workload: same config record as the GPU arm
+    import bench
+    assert d["config"] == bench.headline_config(32, 1000, 320000, 1)

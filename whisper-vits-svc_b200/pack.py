@@ -63,6 +63,54 @@ def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
     return img.view(torch.float32).reshape(-1)
 
 
+S2D_WIDTH = 160   # K' = N' = C * r of the space-to-depth AMP links (csrc/amp_s2d.cu)
+
+
+def s2d_factor(c: int) -> int:
+    """Time samples folded into the channel dimension so that C * r = 160 (0 = stage not eligible)."""
+    return S2D_WIDTH // c if c and S2D_WIDTH % c == 0 and S2D_WIDTH // c in (4, 8, 16) else 0
+
+
+def s2d_taps(k: int, dil: int, r: int):
+    """Row offsets m = -mlo .. mhi of the block-Toeplitz form of a 'same' Conv1d(k, dilation) over rows of r
+    samples: output sample r*tau + po needs input samples r*tau + po + j*dil - P, P = dil*(k-1)/2."""
+    P = dil * (k - 1) // 2
+    mlo = -((-P) // r)             # ceil(P / r)
+    mhi = (r - 1 + P) // r
+    return mlo, mhi
+
+
+def conv_s2d_matrices(w: torch.Tensor, dil: int, r: int) -> torch.Tensor:
+    """[C, C, k] -> [ntaps, N' = C*r, K' = C*r] fp32 block-Toeplitz matrices W_m with
+    y'[tau][(co, po)] = sum_m sum_(ci, pi) W_m[(co, po)][(ci, pi)] * x'[tau + m][(ci, pi)],
+    x'[tau][(c, p)] = x[c][r*tau + p] (index = c*r + p): the dilated Conv1d as `ntaps` dense 160 x 160
+    products over rows of r consecutive samples (csrc/amp_s2d.cu; vits_decoder/bigv.py:22-39)."""
+    cout, cin, k = w.shape
+    P = dil * (k - 1) // 2
+    mlo, mhi = s2d_taps(k, dil, r)
+    W = torch.zeros(mlo + mhi + 1, cout, r, cin, r, dtype=torch.float32)
+    for j in range(k):
+        off = j * dil - P                      # input sample offset of tap j
+        for po in range(r):
+            m, pi = divmod(po + off, r)        # r*m + pi = po + off
+            W[m + mlo, :, po, :, pi] += w[:, :, j]
+    return W.reshape(mlo + mhi + 1, cout * r, cin * r)
+
+
+def pack_conv_s2d(w: torch.Tensor, dil: int, r: int) -> torch.Tensor:
+    """The matrices of conv_s2d_matrices as bf16 hi/lo tensor-core tiles [ntaps][2 (hi, lo)][K'/8][N'][8]
+    (K-major panel layout of csrc/tc.cuh: one (tap, part) = one contiguous 51,200-byte bulk copy),
+    returned as a float32 view of the bytes."""
+    W = conv_s2d_matrices(w, dil, r)                          # [T, n, k]
+    T, n, k = W.shape
+    assert n == S2D_WIDTH and k == S2D_WIDTH, (n, k)
+    hi = W.bfloat16()
+    lo = (W - hi.float()).bfloat16()
+    st = torch.stack([hi, lo], 1)                              # [T, 2, n, k]
+    img = st.view(T, 2, n, k // 8, 8).permute(0, 1, 3, 2, 4).contiguous()   # [T, 2, kc, n, 8]
+    return img.view(torch.float32).reshape(-1)
+
+
 def tc_tiling(cout: int, cin: int):
     """(kch, cin_pad, bn, ntiles) — must match csrc/api.cu:tc_tiling."""
     kch = 64 if cin % 64 == 0 else 32
