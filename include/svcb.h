@@ -244,6 +244,17 @@ int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float*
                         int32_t C, int32_t L, int32_t K, int32_t dilation, int32_t nsplit, void* scratch,
                         size_t scratch_bytes, svcb_stream stream);
 
+/* One `SnakeAlias_in -> Conv1d(C->C, K, dilation) + bias (+ res) [-> SnakeAlias_out]` link of the narrow
+ * generator stages (C = 20 or 10; vits_decoder/bigv.py:50-58) in space-to-depth form (csrc/amp_s2d.cu):
+ * snake_pack_s2d, then the block-Toeplitz tcgen05 convolution whose epilogue writes y (fp32, may be NULL)
+ * and — when y_act != NULL — SnakeAlias_out(result) as the next link's bf16 hi/lo operand image, returned
+ * here decoded to fp32 [B,C,L].  w_s2d = pack.py:pack_conv_s2d image; L % (160/C) == 0. */
+size_t svcb_op_amp_s2d_link_scratch_bytes(int32_t B, int32_t C, int32_t L);
+int svcb_op_amp_s2d_link(const float* x, float* y, const float* res, float* y_act, const float* ea_in,
+                         const float* ib_in, const float* ea_out, const float* ib_out, const float* fu,
+                         const float* fd, const void* w_s2d, const float* bias, int32_t B, int32_t C, int32_t L,
+                         int32_t K, int32_t dilation, void* scratch, size_t scratch_bytes, svcb_stream stream);
+
 /* Self-test of the tcgen05/TMEM plumbing: D[128,N] = A[shift:shift+128, :K] . B[N,K]^T with
  * bf16 operands (row-major, device) and fp32 accumulation in tensor memory. */
 int svcb_op_tc_gemm_selftest(const void* A_bf16, const void* B_bf16, float* D, int32_t R, int32_t N,

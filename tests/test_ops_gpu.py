@@ -197,3 +197,33 @@ def test_conv_tc_epilogues(ops):
     ref2 = torch.relu(F.conv1d(x * mask, w2, b2, padding=1)) * mask + res
     got2 = ops.conv_tc(x.cuda(), w2, b2.cuda(), res=res.cuda(), lengths=lengths, flags=1 | 2, act=1)
     assert max_abs(got2, ref2) <= 2e-4
+
+
+@pytest.mark.parametrize("C,L,K,dil", [(20, 8 * 126 * 2, 3, 1), (20, 8 * 300, 11, 5), (20, 8 * 126, 7, 3), (20, 8 * 5, 11, 3),
+                                       (20, 8, 3, 1), (20, 8 * 1000, 11, 1), (10, 16 * 126, 3, 1), (10, 16 * 200, 11, 5),
+                                       (10, 16 * 3, 7, 5), (10, 16 * 257, 7, 1)])
+def test_amp_s2d_link(ops, sd, C, L, K, dil):
+    """One AMP-block link of the narrow stages in space-to-depth form (csrc/amp_s2d.cu): block-Toeplitz
+    tcgen05 conv (bf16x3) with bias + residual, and the NEXT SnakeAlias computed in the epilogue — both
+    against the oracle's torch ops.  Lengths cover: whole tiles (126 useful rows), ragged last tiles, a
+    single row, items shorter than the Snake / conv reach (sequence-end clamps on both sides at once)."""
+    g = torch.Generator().manual_seed(C * 11 + L + K + dil)
+    B = 2
+    x = torch.randn(B, C, L, generator=g) * 1.5
+    w = torch.randn(C, C, K, generator=g) / (C * K) ** 0.5
+    b = torch.randn(C, generator=g) * 0.1
+    res = torch.randn(B, C, L, generator=g)
+    filt = {"upsample.filter": sd["dec.activation_post.upsample.filter"],
+            "downsample.lowpass.filter": sd["dec.activation_post.downsample.lowpass.filter"]}
+    fa = {"a.act.alpha": torch.randn(C, generator=g) * 0.4, "a.act.beta": torch.randn(C, generator=g) * 0.4,
+          **{"a." + k: v for k, v in filt.items()}}
+    fb = {"b.act.alpha": torch.randn(C, generator=g) * 0.4, "b.act.beta": torch.randn(C, generator=g) * 0.4,
+          **{"b." + k: v for k, v in filt.items()}}
+    ref = F.conv1d(O.snake_alias(fa, "a", x), w, b, dilation=dil, padding=dil * (K - 1) // 2) + res
+    ref_act = O.snake_alias(fb, "b", ref)
+    got, got_act = ops.amp_s2d_link(x.cuda(), fa["a.act.alpha"], fa["a.act.beta"], filt["upsample.filter"],
+                                    filt["downsample.lowpass.filter"], w, b.cuda(), dilation=dil, res=res.cuda(),
+                                    alpha_out=fb["b.act.alpha"], beta_out=fb["b.act.beta"])
+    e1, e2 = max_abs(got, ref), max_abs(got_act, ref_act)
+    print(f"amp_s2d_link C={C} L={L} K={K} d={dil}: conv max-abs {e1:.3e}, next-snake image max-abs {e2:.3e}")
+    assert e1 <= 2e-4 and e2 <= 3e-4

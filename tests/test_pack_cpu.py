@@ -114,3 +114,30 @@ def test_stem_conv2_im2col_equivalence():
     W2 = w.permute(0, 2, 1).reshape(D, 3 * D)
     got = (A @ W2.t() + bias).view(B, n2, D).permute(0, 2, 1)
     assert torch.allclose(got, ref, atol=1e-4)
+
+
+@pytest.mark.parametrize("C,k,dil", [(20, 3, 1), (20, 7, 3), (20, 11, 5), (10, 11, 5), (10, 3, 3), (40, 7, 5)])
+def test_conv_s2d_matrices_are_the_dilated_conv(C, k, dil):
+    """csrc/amp_s2d.cu multiplies rows of r consecutive samples (all channels) by block-Toeplitz matrices:
+    sum over row offsets m of X'[tau + m] @ W_m^T must equal F.conv1d(x, w, dilation, 'same') — checked
+    through the packed bf16 hi/lo image (hi + lo reproduces fp32 weights to ~2^-16 relative)."""
+    import torch.nn.functional as F
+    from whisper_vits_svc_b200 import pack
+    r = pack.s2d_factor(C)
+    assert C * r == pack.S2D_WIDTH
+    g = torch.Generator().manual_seed(C + k + dil)
+    w = torch.randn(C, C, k, generator=g) / (C * k) ** 0.5
+    x = torch.randn(2, C, r * 29, generator=g)
+    ref = F.conv1d(x, w, dilation=dil, padding=dil * (k - 1) // 2)
+    mlo, mhi = pack.s2d_taps(k, dil, r)
+    P = dil * (k - 1) // 2
+    assert mlo == -(-P // r) and mhi == (r - 1 + P) // r and mlo <= 8 and mhi <= 8   # fits the kernel's A panel
+    img = pack.pack_conv_s2d(w, dil, r).view(torch.bfloat16).view(mlo + mhi + 1, 2, 20, 160, 8).float()
+    W = (img[:, 0] + img[:, 1]).permute(0, 2, 1, 3).reshape(mlo + mhi + 1, 160, 160)      # [tap, n, k]
+    assert (W - pack.conv_s2d_matrices(w, dil, r)).abs().max() <= 2e-5
+    X = x.view(2, C, -1, r).permute(0, 2, 1, 3).reshape(2, -1, C * r)
+    n = X.shape[1]
+    Xp = F.pad(X, (0, 0, mlo, mhi))
+    Y = sum(Xp[:, i:i + n] @ W[i].t() for i in range(mlo + mhi + 1))
+    y = Y.view(2, n, C, r).permute(0, 2, 1, 3).reshape(2, C, -1)
+    assert (y - ref).abs().max() <= 1e-4

@@ -284,8 +284,8 @@ static int launch_ab(const AmpBlockParams& p, cudaStream_t s) {
   dim3 grid((p.L + TOUT - 1) / TOUT, p.B);
   char kname[64];
   snprintf(kname, sizeof(kname), "amp_block_fused_c%dk%d", C, p.K);
-  KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B + 6 * 70.0 * C * (double)p.L * p.B,
-                 (p.accum ? 12.0 : 8.0) * C * (double)p.L * p.B);
+  KernelScope ks(kname, s, 2.0 * 6 * C * C * p.K * (double)p.L * p.B, (p.accum ? 12.0 : 8.0) * C * (double)p.L * p.B,
+                 6 * 70.0 * C * (double)p.L * p.B);
   amp_block_fused_kernel<C, K, V><<<grid, AB_THREADS, smem, s>>>(p);
   SVCB_LAUNCH_CHECK("amp_block_fused");
   return SVCB_OK;

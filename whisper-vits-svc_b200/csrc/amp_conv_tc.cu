@@ -157,7 +157,7 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
   const int cp = (C + 15) / 16 * 16, Lp = p8_rows_of(L);
   char kname[64];
   snprintf(kname, sizeof(kname), "snake_pack_c%d", C);
-  KernelScope ks(kname, s, 70.0 * B * C * (double)L, (lo ? 8.0 : 6.0) * B * C * (double)L);
+  KernelScope ks(kname, s, 0.0, (lo ? 8.0 : 6.0) * B * C * (double)L, 70.0 * B * C * (double)L);
   {
     dim3 grid3((Lp + SP3_ROWS - 1) / SP3_ROWS, cp / 8, B);
     auto* h = static_cast<__nv_bfloat16*>(hi);

@@ -28,16 +28,16 @@ int device_sm_count() {
 }
 
 // ----------------------------------------------------------------------------- kernel timing
-struct TimedLaunch { std::string name; cudaEvent_t e0, e1; double flops, bytes; };
+struct TimedLaunch { std::string name; cudaEvent_t e0, e1; double flops, bytes, aux; };
 static bool g_timing = false;
 static std::vector<TimedLaunch> g_timed;
 static std::string g_report;
 
-KernelScope::KernelScope(const char* name, cudaStream_t s, double flops, double bytes)
+KernelScope::KernelScope(const char* name, cudaStream_t s, double flops, double bytes, double aux)
     : slot(-1), stream(s) {
   if (!g_timing) return;
   TimedLaunch t;
-  t.name = name; t.flops = flops; t.bytes = bytes;
+  t.name = name; t.flops = flops; t.bytes = bytes; t.aux = aux;
   if (cudaEventCreate(&t.e0) != cudaSuccess || cudaEventCreate(&t.e1) != cudaSuccess) return;
   cudaEventRecord(t.e0, s);
   g_timed.push_back(t);
@@ -84,9 +84,20 @@ struct UpStage {
 struct ResBlock {
   ConvW c1[3], c2[3];
   const uint8_t *c1_tc[3], *c2_tc[3];  // bf16 hi/lo tensor-core images of the same weights
+  // narrow stages (C * r = 160, r = s2d_r): block-Toeplitz matrices of the same convs (pack.py:pack_conv_s2d)
+  const uint8_t *c1_s2d[3] = {nullptr, nullptr, nullptr}, *c2_s2d[3] = {nullptr, nullptr, nullptr};
+  int s2d_r = 0, s2d_ml1[3], s2d_nt1[3], s2d_ml2[3], s2d_nt2[3];
   SnakeW act[6];
   int k, dil[3];
 };
+
+// must match pack.py:S2D_LINK_FACTORS / s2d_taps
+static int s2d_link_factor(int ch) { return ch == 20 ? 8 : ch == 10 ? 16 : 0; }
+static void s2d_taps(int k, int dil, int r, int& mlo, int& ntaps) {
+  const int P = dil * (k - 1) / 2;
+  mlo = (P + r - 1) / r;
+  ntaps = mlo + (r - 1 + P) / r + 1;
+}
 
 }  // namespace svcb
 
@@ -351,13 +362,45 @@ static int run_flow(const svcb_model* m, Ctx& ctx, const float* z_p, const long 
 
 // ----------------------------------------------------------------------------- generator
 static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* X, float* ACC,
-                         float* T1, float* T2, float* RA, float* RB, void* IMG_HI, void* IMG_LO, int B,
-                         int ch, int L) {
+                         float* T1, float* T2, float* RA, float* RB, void* IMG_HI, void* IMG_LO, void* const* S2D,
+                         int B, int ch, int L) {
   cudaStream_t s = ctx.stream;
   const int nres = m->cfg.n_res;
   const int prec = m->cfg.precision;
   for (int j = 0; j < nres; ++j) {
     const ResBlock& R = m->res[stage * nres + j];
+    if (prec == 3 && R.s2d_r && S2D[0] && L % R.s2d_r == 0) {
+      // narrow stages: every link = block-Toeplitz tcgen05 conv with the next SnakeAlias in its epilogue
+      const int Rp = s2d_rows(L, R.s2d_r);
+      void *ia_hi = S2D[0], *ia_lo = S2D[1], *ib_hi = S2D[2], *ib_lo = S2D[3];
+      RUN(launch_snake_pack_s2d(X, ia_hi, ia_lo, R.act[0].ea, R.act[0].ib, R.act[0].fu, R.act[0].fd, B, ch, L, s));
+      const float* cur = X;
+      for (int d = 0; d < 3; ++d) {
+        AmpS2dParams q;
+        q.B = B; q.C = ch; q.L = L; q.K = R.k; q.Rp = Rp;
+        q.a_hi = ia_hi; q.a_lo = ia_lo; q.o_hi = ib_hi; q.o_lo = ib_lo;
+        q.wpk = R.c1_s2d[d]; q.bias = R.c1[d].b; q.ntaps = R.s2d_nt1[d]; q.mlo = R.s2d_ml1[d];
+        const SnakeW& a2 = R.act[2 * d + 1];
+        q.ea = a2.ea; q.ib = a2.ib; q.fu = a2.fu; q.fd = a2.fd;
+        RUN(launch_amp_s2d_link(q, s));
+        AmpS2dParams q2;
+        q2.B = B; q2.C = ch; q2.L = L; q2.K = R.k; q2.Rp = Rp;
+        q2.a_hi = ib_hi; q2.a_lo = ib_lo;
+        q2.wpk = R.c2_s2d[d]; q2.bias = R.c2[d].b; q2.ntaps = R.s2d_nt2[d]; q2.mlo = R.s2d_ml2[d];
+        q2.res = cur;
+        if (d < 2) {
+          q2.y = (d == 0) ? RA : RB;
+          const SnakeW& a3 = R.act[2 * d + 2];
+          q2.o_hi = ia_hi; q2.o_lo = ia_lo; q2.ea = a3.ea; q2.ib = a3.ib; q2.fu = a3.fu; q2.fd = a3.fd;
+        } else {  // last unit of the block: fold into the stage mean (generator.py:188-194)
+          q2.y = ACC; q2.accum = j > 0;
+          if (j == nres - 1) q2.out_div = (float)nres;
+        }
+        RUN(launch_amp_s2d_link(q2, s));
+        cur = q2.y;
+      }
+      continue;
+    }
     if (prec != 0 && amp_block_fused_supported(ch, R.k, R.dil)) {
       // narrow stages: the whole block (6 convs + 6 SnakeAlias + residuals) in one fp32 kernel
       AmpBlockParams q;
@@ -544,7 +587,25 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
       RUN(launch_conv1d(p, s));
     }
     SVCB_TRY(tap(ctx, SVCB_TAP_GEN_UP0 + i, X, (size_t)B * chn * Ln));
-    SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, IMG_HI, IMG_LO, B, chn, Ln));
+    void* S2D[4] = {nullptr, nullptr, nullptr, nullptr};
+    const int s2r = c.precision == 3 ? s2d_link_factor(chn) : 0;
+    if (s2r && Ln % s2r == 0) {
+      // two ping-pong S2D images (hi, lo each), cleared once per stage: rows outside the sequences are the
+      // convolutions' zero padding and are never written by the link kernels
+      const size_t ib = s2d_image_bytes(B, Ln, s2r);
+      const size_t mark = ctx.off;
+      uint8_t* base = ctx.alloc<uint8_t>(4 * ib);
+      SVCB_TRY(check_ws(ctx));
+      for (int q = 0; q < 4; ++q) S2D[q] = base + (size_t)q * ib;
+      if (!ctx.dry) {
+        KernelScope ks("s2d_image_clear", s, 0.0, 4.0 * ib);
+        SVCB_CUDA_CHECK(cudaMemsetAsync(base, 0, 4 * ib, s));
+      }
+      SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, IMG_HI, IMG_LO, S2D, B, chn, Ln));
+      ctx.off = mark;
+    } else {
+      SVCB_TRY(run_amp_stage(m, ctx, i, X, ACC, T1, T2, RA, RB, IMG_HI, IMG_LO, S2D, B, chn, Ln));
+    }
     SVCB_TRY(tap(ctx, SVCB_TAP_GEN_STAGE0 + i, ACC, (size_t)B * chn * Ln));
     x = ACC; ch = chn; L = Ln;
   }
@@ -682,6 +743,14 @@ static int resolve(svcb_model* m) {
         rb.c1_tc[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c1." + std::to_string(d) + ".tc", tcn));
         rb.c2_tc[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c2." + std::to_string(d) + ".tc", tcn));
       }
+      rb.s2d_r = s2d_link_factor(ch);
+      for (int d = 0; d < 3 && rb.s2d_r; ++d) {
+        s2d_taps(rb.k, rb.dil[d], rb.s2d_r, rb.s2d_ml1[d], rb.s2d_nt1[d]);
+        s2d_taps(rb.k, 1, rb.s2d_r, rb.s2d_ml2[d], rb.s2d_nt2[d]);
+        const uint64_t per_tap = 2ull * 160 * 160 / 2;   // fp32-typed elements of one (hi, lo) pair
+        rb.c1_s2d[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c1." + std::to_string(d) + ".s2d", per_tap * rb.s2d_nt1[d]));
+        rb.c2_s2d[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c2." + std::to_string(d) + ".s2d", per_tap * rb.s2d_nt2[d]));
+      }
       for (int a = 0; a < 6; ++a) rb.act[a] = R.snake(p + ".act." + std::to_string(a), ch);
     }
   }
@@ -739,20 +808,20 @@ void svcb_timing_enable(int32_t on) {
 
 const char* svcb_timing_report(void) {
   // caller must have synchronised the stream(s); one line per kernel name:
-  // name launches total_ms total_flops total_bytes
-  struct Agg { long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  // name launches total_ms total_flops total_bytes total_aux_flops
+  struct Agg { long n = 0; double ms = 0, flops = 0, bytes = 0, aux = 0; };
   std::map<std::string, Agg> agg;
   for (auto& t : g_timed) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, t.e0, t.e1) != cudaSuccess) continue;
     Agg& a = agg[t.name];
-    a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes;
+    a.n++; a.ms += ms; a.flops += t.flops; a.bytes += t.bytes; a.aux += t.aux;
   }
   g_report.clear();
   char buf[256];
   for (auto& kv : agg) {
-    snprintf(buf, sizeof(buf), "%s %ld %.6f %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
-             kv.second.flops, kv.second.bytes);
+    snprintf(buf, sizeof(buf), "%s %ld %.6f %.6e %.6e %.6e\n", kv.first.c_str(), kv.second.n, kv.second.ms,
+             kv.second.flops, kv.second.bytes, kv.second.aux);
     g_report += buf;
   }
   return g_report.c_str();
@@ -942,6 +1011,39 @@ int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float*
   q.wpk = static_cast<const uint8_t*>(w_tc); q.bias = bias;
   q.B = B; q.C = C; q.Cp = (C + 15) / 16 * 16; q.L = L; q.K = K; q.dil = dilation; q.nsplit = nsplit;
   return launch_amp_conv_tc(q, s);
+}
+
+size_t svcb_op_amp_s2d_link_scratch_bytes(int32_t B, int32_t C, int32_t L) {
+  const int r = C > 0 ? 160 / C : 0;
+  if (B <= 0 || L <= 0 || !s2d_link_factor(C) || L % r) return 0;
+  return 4 * ((s2d_image_bytes(B, L, r) + 255) & ~(size_t)255) + 512;
+}
+
+int svcb_op_amp_s2d_link(const float* x, float* y, const float* res, float* y_act, const float* ea_in,
+                         const float* ib_in, const float* ea_out, const float* ib_out, const float* fu,
+                         const float* fd, const void* w_s2d, const float* bias, int32_t B, int32_t C, int32_t L,
+                         int32_t K, int32_t dilation, void* scratch, size_t scratch_bytes, svcb_stream stream) {
+  g_launches = 0;
+  const int r = s2d_link_factor(C);
+  if (!r || B <= 0 || L <= 0 || L % r) { set_error("svcb_op_amp_s2d_link: need C in {20, 10} and L % (160/C) == 0"); return SVCB_E_BAD_SHAPE; }
+  const size_t img = (s2d_image_bytes(B, L, r) + 255) & ~(size_t)255;
+  if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < 4 * img) {
+    set_error("svcb_op_amp_s2d_link: scratch too small or misaligned");
+    return SVCB_E_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* b0 = static_cast<char*>(scratch);
+  SVCB_CUDA_CHECK(cudaMemsetAsync(b0, 0, 4 * img, s));
+  SVCB_TRY(launch_snake_pack_s2d(x, b0, b0 + img, ea_in, ib_in, fu, fd, B, C, L, s));
+  AmpS2dParams q;
+  q.B = B; q.C = C; q.L = L; q.K = K; q.Rp = s2d_rows(L, r);
+  q.a_hi = b0; q.a_lo = b0 + img;
+  if (y_act) { q.o_hi = b0 + 2 * img; q.o_lo = b0 + 3 * img; q.ea = ea_out; q.ib = ib_out; q.fu = fu; q.fd = fd; }
+  q.wpk = static_cast<const uint8_t*>(w_s2d); q.bias = bias; q.res = res; q.y = y;
+  s2d_taps(K, dilation, r, q.mlo, q.ntaps);
+  SVCB_TRY(launch_amp_s2d_link(q, s));
+  if (y_act) SVCB_TRY(launch_s2d_unpack(q.o_hi, q.o_lo, y_act, B, C, L, s));
+  return SVCB_OK;
 }
 
 int svcb_op_snake_alias(const float* x, float* y, const float* ea, const float* inv_b,

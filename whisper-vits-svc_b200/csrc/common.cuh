@@ -15,7 +15,9 @@ void count_launch();
 // Optional per-kernel CUDA-event timing (svcb_timing_enable): a KernelScope brackets one launch
 // with two events on the launching stream and books its algorithmic FLOPs / bytes under `name`.
 struct KernelScope {
-  KernelScope(const char* name, cudaStream_t s, double flops, double bytes);
+  // flops = SURVEY.md §8(d) algorithmic FLOPs of the launch (conv / GEMM products only), bytes = its
+  // algorithmic HBM bytes, aux = activation work (Snake ~70 FLOP per element) reported separately
+  KernelScope(const char* name, cudaStream_t s, double flops, double bytes, double aux = 0.0);
   ~KernelScope();
   int slot;
   cudaStream_t stream;
@@ -134,6 +136,30 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
                       const float* fd, int B, int C, int L, cudaStream_t s);
 size_t p8_image_bytes(int B, int C, int L);
 int p8_rows(int L);
+
+// ----------------------------------------------------------------------------- space-to-depth AMP links (C = 20, 10)
+struct AmpS2dParams {
+  const void* a_hi = nullptr;   // input S2D image (bf16 hi) [B][20][Rp][8] — SnakeAlias already applied
+  const void* a_lo = nullptr;
+  void* o_hi = nullptr;         // output S2D image = SnakeAlias_next(result), or null
+  void* o_lo = nullptr;
+  const uint8_t* wpk = nullptr; // bf16 [ntaps][2 (hi, lo)][20][160][8]  (pack.py:pack_conv_s2d)
+  const float* bias = nullptr;  // [C]
+  const float* res = nullptr;   // residual [B, C, L] fp32 or null
+  float* y = nullptr;           // fp32 result [B, C, L] or null
+  const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;   // Snake of the output image
+  int B = 0, C = 0, L = 0, K = 0;   // K = taps of the original conv (bookkeeping only)
+  int Rp = 0;                   // image rows per (item, octet) = s2d_rows(L, r)
+  int ntaps = 0, mlo = 0;       // Toeplitz row offsets -mlo .. ntaps-1-mlo (pack.py:s2d_taps)
+  int accum = 0;                // y = y_old + v
+  float out_div = 0.f;          // then / out_div when != 0
+};
+int launch_amp_s2d_link(const AmpS2dParams& p, cudaStream_t s);
+int launch_snake_pack_s2d(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
+                          const float* fd, int B, int C, int L, cudaStream_t s);
+int launch_s2d_unpack(const void* hi, const void* lo, float* y, int B, int C, int L, cudaStream_t s);
+int s2d_rows(int L, int r);
+size_t s2d_image_bytes(int B, int L, int r);
 
 // ----------------------------------------------------------------------------- fused AMP block (C = 10, 20)
 struct AmpBlockParams {

@@ -95,6 +95,37 @@ def amp_conv_tc(x, alpha, beta, fu, fd, weight, bias, dilation=1, res=None, nspl
     return y
 
 
+def amp_s2d_link(x, alpha_in, beta_in, fu, fd, weight, bias, dilation=1, res=None, alpha_out=None, beta_out=None):
+    """SnakeAlias_in -> Conv1d(C->C, K, dilation, 'same') + bias (+res) [-> SnakeAlias_out] in space-to-depth
+    form (C = 20 / 10).  Returns (y, y_act): the fp32 result and, when alpha_out is given, the next link's
+    operand image decoded back to fp32."""
+    x = _c(x)
+    B, C, L = x.shape
+    K = weight.shape[-1]
+    r = pack.s2d_factor(C)
+
+    def snake_params(a, b):
+        return (_c(torch.exp(a.float().cpu()).to(x.device)), _c((1.0 / (torch.exp(b.float().cpu()) + 1e-9)).to(x.device)))
+
+    ea_i, ib_i = snake_params(alpha_in, beta_in)
+    ea_o, ib_o = snake_params(alpha_out, beta_out) if alpha_out is not None else (None, None)
+    fu, fd = _c(fu.reshape(-1).to(x.device)), _c(fd.reshape(-1).to(x.device))
+    w = pack.pack_conv_s2d(weight.detach().cpu().float(), dilation, r).to(x.device)
+    b = _c(bias)
+    rs = _c(res) if res is not None else None
+    y = torch.empty_like(x)
+    y_act = torch.empty_like(x) if alpha_out is not None else None
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.svcb_op_amp_s2d_link_scratch_bytes(B, C, L)), dtype=torch.uint8, device=x.device)
+    st = lib.svcb_op_amp_s2d_link(x.data_ptr(), y.data_ptr(), rs.data_ptr() if rs is not None else None,
+                                  y_act.data_ptr() if y_act is not None else None, ea_i.data_ptr(), ib_i.data_ptr(),
+                                  ea_o.data_ptr() if ea_o is not None else None, ib_o.data_ptr() if ib_o is not None else None,
+                                  fu.data_ptr(), fd.data_ptr(), w.data_ptr(), b.data_ptr(), B, C, L, K, dilation,
+                                  scratch.data_ptr(), scratch.numel(), _s())
+    _lib.check(st, "svcb_op_amp_s2d_link")
+    return y, y_act
+
+
 def conv_tc(x, weight, bias=None, dilation=1, res=None, lengths=None, nsplit=3, flags=0, act=0):
     """Stride-1 'same' Conv1d on the tensor cores; weight in torch layout [Cout,Cin,K]."""
     x = _c(x)

@@ -64,6 +64,7 @@ def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
 
 
 S2D_WIDTH = 160   # K' = N' = C * r of the space-to-depth AMP links (csrc/amp_s2d.cu)
+S2D_LINK_FACTORS = (8, 16)   # factors csrc/amp_s2d.cu implements (C = 20, 10); must match api.cu:s2d_link_factor
 
 
 def s2d_factor(c: int) -> int:
@@ -236,6 +237,9 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
     n_blocks = cfg["n_ups"] * cfg["n_res"]
     for n in range(n_blocks):
         p = f"dec.resblocks.{n}"
+        stage, j = divmod(n, cfg["n_res"])
+        ch = cfg["gen_initial_channel"] >> (stage + 1)
+        r = s2d_factor(ch) if s2d_factor(ch) in S2D_LINK_FACTORS else 0
         for d in range(3):
             w1 = fold_weight_norm(sd, f"{p}.convs1.{d}")
             w2 = fold_weight_norm(sd, f"{p}.convs2.{d}")
@@ -243,6 +247,9 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
             conv(f"dec.res.{n}.c2.{d}", w2, sd[f"{p}.convs2.{d}.bias"])
             put(f"dec.res.{n}.c1.{d}.tc", pack_conv_tc(w1))
             put(f"dec.res.{n}.c2.{d}.tc", pack_conv_tc(w2))
+            if r:   # narrow stages: block-Toeplitz matrices for csrc/amp_s2d.cu
+                put(f"dec.res.{n}.c1.{d}.s2d", pack_conv_s2d(w1, cfg["res_dilations"][j][d], r))
+                put(f"dec.res.{n}.c2.{d}.s2d", pack_conv_s2d(w2, 1, r))
         for a in range(6):
             _snake(put, f"dec.res.{n}.act.{a}", sd, f"{p}.activations.{a}")
     _snake(put, "dec.post.act", sd, "dec.activation_post")
