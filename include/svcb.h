@@ -250,6 +250,9 @@ int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float*
  * and — when y_act != NULL — SnakeAlias_out(result) as the next link's bf16 hi/lo operand image, returned
  * here decoded to fp32 [B,C,L].  w_s2d = pack.py:pack_conv_s2d image; L % (160/C) == 0. */
 size_t svcb_op_amp_s2d_link_scratch_bytes(int32_t B, int32_t C, int32_t L);
+/* Debugging hook (profiling scripts): when dev_buf != NULL, CTA 0 of every following amp_s2d link launch
+ * writes clock64() stamps of its first 32 tiles into dev_buf ([32][16] int64); NULL switches it off. */
+void svcb_debug_s2d_trace(void* dev_buf);
 int svcb_op_amp_s2d_link(const float* x, float* y, const float* res, float* y_act, const float* ea_in,
                          const float* ib_in, const float* ea_out, const float* ib_out, const float* fu,
                          const float* fd, const void* w_s2d, const float* bias, int32_t B, int32_t C, int32_t L,

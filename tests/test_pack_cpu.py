@@ -132,7 +132,9 @@ def test_conv_s2d_matrices_are_the_dilated_conv(C, k, dil):
     mlo, mhi = pack.s2d_taps(k, dil, r)
     P = dil * (k - 1) // 2
     assert mlo == -(-P // r) and mhi == (r - 1 + P) // r and mlo <= 8 and mhi <= 8   # fits the kernel's A panel
-    img = pack.pack_conv_s2d(w, dil, r).view(torch.bfloat16).view(mlo + mhi + 1, 2, 20, 160, 8).float()
+    packed = pack.pack_conv_s2d(w, dil, r).view(pack.S2D_REPLICAS, -1)
+    assert all(torch.equal(packed[0], packed[i]) for i in range(1, pack.S2D_REPLICAS))   # replicas for L2 spreading
+    img = packed[0].contiguous().view(torch.bfloat16).view(mlo + mhi + 1, 2, 20, 160, 8).float()
     W = (img[:, 0] + img[:, 1]).permute(0, 2, 1, 3).reshape(mlo + mhi + 1, 160, 160)      # [tap, n, k]
     assert (W - pack.conv_s2d_matrices(w, dil, r)).abs().max() <= 2e-5
     X = x.view(2, C, -1, r).permute(0, 2, 1, 3).reshape(2, -1, C * r)

@@ -41,7 +41,7 @@ constexpr int PADR = 16;          // zero rows in front of every (item, octet) o
 constexpr int TILE = 128;         // accumulator rows per tile
 constexpr uint32_t A_PART = KC * RA * 16;       // 46,080 B
 constexpr uint32_t W_SLOT = KC * N * 16;        // 51,200 B: one (tap, hi|lo) matrix
-constexpr uint32_t STG_BYTES = 32768;           // Snake staging strips (4 groups)
+constexpr uint32_t STG_BYTES = 64 + 4 * TILE * 16 * 4 + 64 + 4 * 64 * 4;   // 4 sample strips (+ guards) + 4 edge buffers
 constexpr uint32_t SMEM = 2 * A_PART + 2 * W_SLOT + STG_BYTES;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
@@ -59,8 +59,10 @@ size_t s2d_image_bytes(int B, int L, int r) { return (size_t)B * s2d::KC * s2d_r
 // ------------------------------------------------------------------------------------------------ Snake
 // 8 outputs n0 .. n0+7 from the 24 inputs xw[0..24) = x[n0-8 .. n0+16)  (same arithmetic as
 // amp_conv_tc.cu:sp3_run; alias/resample.py:25-33, alias/act.py:79-92, alias/filter.py:86-94)
+// first / last: the run starts at sample 0 / ends at sample L-1 — the 2x signal is then replicate-padded
+// (alias/filter.py:90-91): values in front of v[0] (vv[0..6)) / behind v[2L-1] (vv[22..28)) repeat it.
 __device__ __forceinline__ void s2d_snake8(const float (&x)[24], const float (&fu)[12], const float (&fdn)[12],
-                                           float a_, float b_, float (&o)[8]) {
+                                           float a_, float b_, float (&o)[8], bool first = false, bool last = false) {
   float vv[28];
 #pragma unroll
   for (int p = 0; p < 14; ++p) {
@@ -74,6 +76,14 @@ __device__ __forceinline__ void s2d_snake8(const float (&x)[24], const float (&f
     vv[2 * p] = fmaf(b_, se * se, ue);
     vv[2 * p + 1] = fmaf(b_, so * so, uo);
   }
+  if (first) {
+#pragma unroll
+    for (int j = 0; j < 6; ++j) vv[j] = vv[6];
+  }
+  if (last) {
+#pragma unroll
+    for (int j = 22; j < 28; ++j) vv[j] = vv[21];
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     float acc = 0.f;
@@ -81,25 +91,6 @@ __device__ __forceinline__ void s2d_snake8(const float (&x)[24], const float (&f
     for (int k = 0; k < 12; ++k) acc = fmaf(vv[2 * i + 1 + k], fdn[k], acc);
     o[i] = acc;
   }
-}
-
-// One output sample n where a tap crosses a sequence end: replicate-clamped indices (the reference pads x
-// by replication before the transposed conv and the 2x signal before the decimating conv).
-// `xs(s)` returns sample s of the channel (0 <= s < L).  Rare path (first / last rows of an item).
-template <typename F>
-__device__ __noinline__ float s2d_snake1_edge(F xs, int n, int L, const float* f_up, const float* f_dn, float a_, float b_) {
-  const int mhi = 2 * L - 1;
-  float acc = 0.f;
-  for (int k = 0; k < 12; ++k) {
-    const int m = min(max(2 * n - 5 + k, 0), mhi);
-    const int a = m >> 1, q = m & 1;
-    float u = 0.f;
-    for (int d = q; d < q + 6; ++d) u = fmaf(xs(min(max(a - 3 + d, 0), L - 1)), f_up[11 + q - 2 * d], u);
-    u *= 2.f;
-    const float sn = snake_sin(u * a_);
-    acc = fmaf(fmaf(b_, sn * sn, u), f_dn[k], acc);
-  }
-  return acc;
 }
 
 __device__ __forceinline__ void s2d_store_octet(__nv_bfloat16* hi, __nv_bfloat16* lo, long long row_elem,
@@ -133,21 +124,21 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
   const float* xr = x + ((long long)b * C + c) * L;
   const int n0 = run * 8;
   const float a_ = __ldg(ea + c), b_ = __ldg(inv_b + c);
-  float out[8];
-  if (n0 - 8 >= 0 && n0 + 16 <= L) {
-    float xw[24], fu[12], fdn[12];
+  float out[8], xw[24], fu[12], fdn[12];
 #pragma unroll
-    for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }
+  for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }
+  const bool first = n0 == 0, last = n0 + 8 == L;
+  if (n0 - 8 >= 0 && n0 + 16 <= L) {
 #pragma unroll
     for (int q = 0; q < 6; ++q) {
       const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr + n0 - 8) + q);
       xw[4 * q] = t4.x; xw[4 * q + 1] = t4.y; xw[4 * q + 2] = t4.z; xw[4 * q + 3] = t4.w;
     }
-    s2d_snake8(xw, fu, fdn, a_, b_, out);
-  } else {
+  } else {   // within 8 samples of a sequence end: replicate padding of x (alias/resample.py:28) = clamped loads
 #pragma unroll
-    for (int i = 0; i < 8; ++i) out[i] = s2d_snake1_edge([&](int s) { return __ldg(xr + s); }, n0 + i, L, f_up, f_dn, a_, b_);
+    for (int j = 0; j < 24; ++j) xw[j] = __ldg(xr + min(max(n0 - 8 + j, 0), L - 1));
   }
+  s2d_snake8(xw, fu, fdn, a_, b_, out, first, last);
   const long long row_elem = ((((long long)b * s2d::KC + o) * Rp) + s2d::PADR + row) * 8;
   s2d_store_octet(hi, lo, row_elem, out);
 }
@@ -195,6 +186,8 @@ int launch_s2d_unpack(const void* hi, const void* lo, float* y, int B, int C, in
 //   MMA warp       per tap: A_hi x W_hi, A_lo x W_hi, A_hi x W_lo — 30 MMAs (N = 160) with compile-time
 //                  descriptor offsets (no per-MMA integer work in the issuing thread)
 //   16 epilogue warps = 4 column groups x 4 TMEM lane quadrants: group g owns channels c = g (mod 4)
+#define S2D_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 32 && lane == 0) p.trace[it * 16 + (slot)] = clock64(); } while (0)
+
 template <int R>
 __global__ void __launch_bounds__(s2d::THREADS, 1)
 amp_s2d_link_kernel(const AmpS2dParams p) {
@@ -202,7 +195,6 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t a_full, a_empty, w_full[2], w_empty[2], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
-  __shared__ float s_fu[12], s_fd[12];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = tc::warp_uniform_idx();
@@ -223,7 +215,6 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
     }
     tc::fence_barrier_init();
   }
-  if (tid < 12 && p.o_hi) { s_fu[tid] = __ldg(p.fu + tid); s_fd[tid] = __ldg(p.fd + tid); }
   __syncwarp();
   if (warp == EPI_WARPS) tc::tmem_alloc(&tmem_slot, 512);
   tc::fence_before_sync();
@@ -235,21 +226,30 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
     // ------------------------------------------------------------------------------------ producer
     if (tc::elect_one()) {
       const uint8_t* img[2] = {reinterpret_cast<const uint8_t*>(p.a_hi), reinterpret_cast<const uint8_t*>(p.a_lo)};
+      // this CTA's copy of the matrices (identical replicas; spreads the hot L2 lines, see pack.py)
+      const uint8_t* wsrc = p.wpk + (size_t)(blockIdx.x % kS2dReplicas) * (size_t)(2 * p.ntaps) * W_SLOT;
       int it = 0, wi = 0;
       for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
         const int b = tile / tpi, t = tile - b * tpi;
         const long long row0 = (long long)t * S - HS - A_OFF + PADR;     // image row of A-panel row 0 (>= 6)
-        if (it >= 1) tc::mbar_wait(&a_empty, (uint32_t)((it - 1) & 1));
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 16 + 0] = clock64();
+        if (it >= 1) tc::mbar_wait_parked(&a_empty, (uint32_t)((it - 1) & 1));
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 16 + 1] = clock64();
         tc::mbar_arrive_expect_tx(&a_full, 2 * A_PART);
         for (int part = 0; part < 2; ++part)
           for (int kc = 0; kc < KC; ++kc)
             tc::bulk_g2s(Abase + (size_t)part * A_PART + (size_t)kc * RA * 16,
                          img[part] + ((((long long)b * KC + kc) * p.Rp) + row0) * 16, RA * 16, &a_full);
+        if (p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 16 + 2] = clock64();
         for (int c = 0; c < 2 * p.ntaps; ++c, ++wi) {
           const int st = wi & 1;
-          if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          if (wi >= 2) tc::mbar_wait_parked(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          if (c == 0 && p.trace && blockIdx.x == 0 && it < 32) p.trace[it * 16 + 3] = clock64();
           tc::mbar_arrive_expect_tx(&w_full[st], W_SLOT);
-          tc::bulk_g2s(Wbase + (size_t)st * W_SLOT, p.wpk + (size_t)c * W_SLOT, W_SLOT, &w_full[st]);
+#pragma unroll
+          for (int piece = 0; piece < 4; ++piece)    // four requests in flight per matrix instead of one long one
+            tc::bulk_g2s(Wbase + (size_t)st * W_SLOT + piece * (W_SLOT / 4), wsrc + (size_t)c * W_SLOT + piece * (W_SLOT / 4),
+                         W_SLOT / 4, &w_full[st]);
         }
       }
     }
@@ -264,8 +264,11 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
     int it = 0, wi = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
-      tc::mbar_wait(&a_full, (uint32_t)(it & 1));
-      if (it >= 2) tc::mbar_wait(&t_empty[acc], (uint32_t)(((it >> 1) - 1) & 1));
+      S2D_TRACE(4);
+      tc::mbar_wait_parked(&a_full, (uint32_t)(it & 1));
+      S2D_TRACE(5);
+      if (it >= 2) tc::mbar_wait_parked(&t_empty[acc], (uint32_t)(((it >> 1) - 1) & 1));
+      S2D_TRACE(6);
       tc::fence_after_sync();
       const uint32_t d_tmem = tmem + (uint32_t)acc * ACC_STRIDE;
       for (int tap = 0; tap < p.ntaps; ++tap) {
@@ -273,7 +276,9 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
         const uint32_t a_h = (uint32_t)adh + arow, a_l = (uint32_t)adl + arow;
         {  // W_hi of this tap: A_hi x W_hi, A_lo x W_hi
           const int st = wi & 1;
-          tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+          tc::mbar_wait_parked(&w_full[st], (uint32_t)((wi >> 1) & 1));
+          if (tap == 0) S2D_TRACE(7);
+          if (tap == 1) S2D_TRACE(8);
           tc::fence_after_sync();
           const uint32_t bw = (uint32_t)(st ? bd1 : bd0);
           if (tc::elect_one()) {
@@ -288,7 +293,7 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
         }
         {  // W_lo of this tap: A_hi x W_lo
           const int st = wi & 1;
-          tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+          tc::mbar_wait_parked(&w_full[st], (uint32_t)((wi >> 1) & 1));
           tc::fence_after_sync();
           const uint32_t bw = (uint32_t)(st ? bd1 : bd0);
           if (tc::elect_one()) {
@@ -303,23 +308,18 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
         tc::mma_commit(&a_empty);
         tc::mma_commit(&t_full[acc]);
       }
+      S2D_TRACE(9);
     }
   } else {
     // ------------------------------------------------------------------------------------ epilogue
     const int q = warp & 3, g = warp >> 2;
     const int row = q * 32 + lane;
-    constexpr int NBUF = R == 8 ? 2 : 1;
-    constexpr int STRIP = TILE * R;                              // floats per channel strip
-    float* stg_g = Stg + (size_t)g * (STG_BYTES / 16);
-    float fu[12], fdn[12];
-    if (p.o_hi) {
-#pragma unroll
-      for (int k = 0; k < 12; ++k) { fu[k] = 2.f * s_fu[k]; fdn[k] = s_fd[k]; }
-    }
+    float* stg_g = Stg + 16 + (size_t)g * (TILE * 16);          // one strip of up to 128 x 16 samples per group
+    float* edge_g = Stg + 16 + 4 * (TILE * 16) + 16 + g * 64;      // [4 warps][lane 0: 5 | lane 31: 5] Snake values
     __nv_bfloat16* o_hi = static_cast<__nv_bfloat16*>(p.o_hi);
     __nv_bfloat16* o_lo = static_cast<__nv_bfloat16*>(p.o_lo);
     const bool do_div = p.out_div != 0.f;
-    int it = 0, nbar = 0;
+    int it = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       const int acc = it & 1;
       const int b = tile / tpi, t = tile - b * tpi;
@@ -327,10 +327,25 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
       const int tau = tau0 + row;
       const bool valid = tau >= 0 && tau < nrows;
       const bool useful = valid && row >= HS && row < TILE - HS;
-      tc::mbar_wait(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      // residual rows are independent of the accumulator: the first channel's are requested before the
+      // wait, every later channel's one channel ahead (their latency was 19 % of all stall samples)
+      const bool has_res = p.res != nullptr && valid;
+      const long long xrow = (long long)b * p.C * p.L + (long long)tau * R;
+      float4 rcur[R / 4], rnext[R / 4];
+      auto load_res = [&](int c, float4 (&dst)[R / 4]) {
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < R / 4; ++j) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + xrow + (long long)c * p.L) + j);
+        }
+      };
+      load_res(g, rcur);
+      if (warp == 0) S2D_TRACE(10);
+      tc::mbar_wait_parked(&t_full[acc], (uint32_t)((it >> 1) & 1));
+      if (warp == 0) S2D_TRACE(11);
       tc::fence_after_sync();
       const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_STRIDE;
       for (int c = g; c < p.C; c += 4) {
+        if (c + 4 < p.C) load_res(c + 4, rnext);
         float v[R];
         {
           uint32_t u[R];
@@ -341,14 +356,15 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
 #pragma unroll
           for (int j = 0; j < R; ++j) v[j] = __uint_as_float(u[j]) + bias;
         }
-        const long long xoff = ((long long)b * p.C + c) * p.L + (long long)tau * R;
-        if (p.res && valid) {
+        const long long xoff = xrow + (long long)c * p.L;
+        if (has_res) {
 #pragma unroll
           for (int j = 0; j < R / 4; ++j) {
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(p.res + xoff) + j);
-            v[4 * j] += r4.x; v[4 * j + 1] += r4.y; v[4 * j + 2] += r4.z; v[4 * j + 3] += r4.w;
+            v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
           }
         }
+#pragma unroll
+        for (int j = 0; j < R / 4; ++j) rcur[j] = rnext[j];
         if (p.y && useful) {
           float4* yp = reinterpret_cast<float4*>(p.y + xoff);
 #pragma unroll
@@ -361,43 +377,98 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
           }
         }
         if (p.o_hi) {
-          float* strip = stg_g + (NBUF == 2 ? (nbar & 1) * STRIP : 0);
+          // SnakeAlias of the result, written as the next link's operand image.  A row owns R consecutive
+          // samples of the channel: it up-samples + applies Snake to ITS 2R values only (the 4 + 4 samples
+          // it needs from the neighbouring rows come from the shared strip), then the 5 + 5 Snake values of
+          // the neighbouring rows that its decimation filter reaches arrive by warp shuffle (lanes 0 / 31:
+          // through a 64-float edge buffer), so nothing is computed twice: 30 FMA + 2 sin per sample
+          // instead of 46 + 3.5 for the register-run form with recomputed halos.
+          float* strip = stg_g;
 #pragma unroll
           for (int j = 0; j < R / 4; ++j)
             *reinterpret_cast<float4*>(strip + row * R + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-          ++nbar;
+          const float a_ = __ldg(p.ea + c), b_ = __ldg(p.ib + c);
+          float vall[2 * R + 10];                                    // [prev 5 | own 2R | next 5]
+          {
+            float xw[R + 8];                                         // samples -4 .. R+3 relative to the row's first
+            float4 l4 = *reinterpret_cast<const float4*>(strip + row * R - 4);   // (row 0 / 127 read 16 B outside the
+            float4 r4 = *reinterpret_cast<const float4*>(strip + row * R + R);   //  strip: halo rows, values unused)
+            // sequence ends: the reference pads x by replication before up-sampling (alias/resample.py:28)
+            if (tau == 0) l4 = make_float4(v[0], v[0], v[0], v[0]);
+            if (tau == nrows - 1) r4 = make_float4(v[R - 1], v[R - 1], v[R - 1], v[R - 1]);
+            xw[0] = l4.x; xw[1] = l4.y; xw[2] = l4.z; xw[3] = l4.w;
+#pragma unroll
+            for (int j = 0; j < R; ++j) xw[4 + j] = v[j];
+            xw[R + 4] = r4.x; xw[R + 5] = r4.y; xw[R + 6] = r4.z; xw[R + 7] = r4.w;
+#pragma unroll
+            for (int a = 0; a < R; ++a) {
+              float ue = xw[a + 1] * p.fu2[11];
+              ue = fmaf(xw[a + 2], p.fu2[9], ue); ue = fmaf(xw[a + 3], p.fu2[7], ue); ue = fmaf(xw[a + 4], p.fu2[5], ue);
+              ue = fmaf(xw[a + 5], p.fu2[3], ue); ue = fmaf(xw[a + 6], p.fu2[1], ue);
+              float uo = xw[a + 2] * p.fu2[10];
+              uo = fmaf(xw[a + 3], p.fu2[8], uo); uo = fmaf(xw[a + 4], p.fu2[6], uo); uo = fmaf(xw[a + 5], p.fu2[4], uo);
+              uo = fmaf(xw[a + 6], p.fu2[2], uo); uo = fmaf(xw[a + 7], p.fu2[0], uo);
+              const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);
+              vall[5 + 2 * a] = fmaf(b_, se * se, ue);
+              vall[5 + 2 * a + 1] = fmaf(b_, so * so, uo);
+            }
+          }
+          float* edge = edge_g + q * 16;
+          if (lane == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) edge[i] = vall[5 + i];
+          }
+          if (lane == 31) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) edge[8 + i] = vall[5 + 2 * R - 5 + i];
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            vall[i] = __shfl_up_sync(0xffffffffu, vall[2 * R + i], 1);          // previous row's last five
+            vall[2 * R + 5 + i] = __shfl_down_sync(0xffffffffu, vall[5 + i], 1);  // next row's first five
+          }
+          if (lane == 0 && q > 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) vall[i] = edge_g[(q - 1) * 16 + 8 + i];
+          }
+          if (lane == 31 && q < 3) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) vall[2 * R + 5 + i] = edge_g[(q + 1) * 16 + i];
+          }
+          // ... and the 2x signal by replication before decimating (alias/filter.py:90-91)
+          if (tau == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) vall[i] = vall[5];
+          }
+          if (tau == nrows - 1) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) vall[2 * R + 5 + i] = vall[2 * R + 4];
+          }
           if (useful) {
-            const float a_ = __ldg(p.ea + c), b_ = __ldg(p.ib + c);
 #pragma unroll
             for (int h = 0; h < R / 8; ++h) {
-              const int n0 = row * R + 8 * h;                       // strip index of the run's first sample
-              const int s0 = tau * R + 8 * h;                       // its sample index in the sequence
-              float o[8];
-              if (s0 - 6 >= 0 && s0 + 13 <= p.L - 1) {
-                float xw[24];
+              float oh[8];
 #pragma unroll
-                for (int k4 = 0; k4 < 6; ++k4) {
-                  const float4 t4 = *reinterpret_cast<const float4*>(strip + n0 - 8 + 4 * k4);
-                  xw[4 * k4] = t4.x; xw[4 * k4 + 1] = t4.y; xw[4 * k4 + 2] = t4.z; xw[4 * k4 + 3] = t4.w;
-                }
-                s2d_snake8(xw, fu, fdn, a_, b_, o);
-              } else {
-                const int sh = tau0 * R;                            // sample index of strip position 0
+              for (int i = 0; i < 8; ++i) {
+                const int n = 8 * h + i;                            // out[n] = sum_k V[2n - 5 + k] f[k], V[j] = vall[j + 5]
+                float accd = vall[2 * n] * p.fdn[0];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
-                  o[i] = s2d_snake1_edge([&](int s) { return strip[s - sh]; }, s0 + i, p.L, s_fu, s_fd, a_, b_);
+                for (int k = 1; k < 12; ++k) accd = fmaf(vall[2 * n + k], p.fdn[k], accd);
+                oh[i] = accd;
               }
               const int oc = c * (R / 8) + h;
               const long long row_elem = ((((long long)b * KC + oc) * p.Rp) + PADR + tau) * 8;
-              s2d_store_octet(o_hi, o_lo, row_elem, o);
+              s2d_store_octet(o_hi, o_lo, row_elem, oh);
             }
           }
-          if (NBUF == 1) asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
         }
       }
       tc::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&t_empty[acc])) : "memory");
+      if (warp == 0) S2D_TRACE(12);
+      if (warp == 15) S2D_TRACE(13);
     }
   }
   tc::fence_before_sync();
@@ -405,7 +476,12 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
   if (warp == s2d::EPI_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
-int launch_amp_s2d_link(const AmpS2dParams& p, cudaStream_t s) {
+static long long* g_s2d_trace = nullptr;
+void s2d_set_trace(long long* dev_buf) { g_s2d_trace = dev_buf; }
+
+int launch_amp_s2d_link(const AmpS2dParams& p_in, cudaStream_t s) {
+  AmpS2dParams p = p_in;
+  p.trace = g_s2d_trace;
   const int r = p.C > 0 ? s2d::N / p.C : 0;
   if (p.B <= 0 || p.L <= 0 || p.C * r != s2d::N || (r != 8 && r != 16) || p.L % r) {
     set_error("amp_s2d_link: unsupported shape (need C * r = 160 with r in {8, 16} and L % r == 0)");

@@ -63,7 +63,13 @@ static void tc_tiling(ConvW& w) {
   w.ntiles = (cp16 + 255) / 256;
   w.bn = ((cp16 + w.ntiles - 1) / w.ntiles + 15) / 16 * 16;
 }
-struct SnakeW { const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr; };
+struct SnakeW {
+  const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;
+  float fu_h[12] = {0}, fd_h[12] = {0};   // host copies of the 12 + 12 alias-filter taps (read back once at model creation)
+};
+static void snake_taps_to(const SnakeW& w, AmpS2dParams& q) {
+  for (int k = 0; k < 12; ++k) { q.fu2[k] = 2.f * w.fu_h[k]; q.fdn[k] = w.fd_h[k]; }
+}
 
 struct EncLayer {
   ConvW qkv, o, ffn1, ffn2;
@@ -382,6 +388,7 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
         q.wpk = R.c1_s2d[d]; q.bias = R.c1[d].b; q.ntaps = R.s2d_nt1[d]; q.mlo = R.s2d_ml1[d];
         const SnakeW& a2 = R.act[2 * d + 1];
         q.ea = a2.ea; q.ib = a2.ib; q.fu = a2.fu; q.fd = a2.fd;
+        snake_taps_to(a2, q);
         RUN(launch_amp_s2d_link(q, s));
         AmpS2dParams q2;
         q2.B = B; q2.C = ch; q2.L = L; q2.K = R.k; q2.Rp = Rp;
@@ -392,6 +399,7 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
           q2.y = (d == 0) ? RA : RB;
           const SnakeW& a3 = R.act[2 * d + 2];
           q2.o_hi = ia_hi; q2.o_lo = ia_lo; q2.ea = a3.ea; q2.ib = a3.ib; q2.fu = a3.fu; q2.fd = a3.fd;
+          snake_taps_to(a3, q2);
         } else {  // last unit of the block: fold into the stage mean (generator.py:188-194)
           q2.y = ACC; q2.accum = j > 0;
           if (j == nres - 1) q2.out_div = (float)nres;
@@ -649,6 +657,11 @@ struct Resolver {
     SnakeW s;
     s.ea = get(prefix + ".ea", ch); s.ib = get(prefix + ".ib", ch);
     s.fu = get(prefix + ".fu", 12); s.fd = get(prefix + ".fd", 12);
+    if (s.fu && s.fd && (cudaMemcpy(s.fu_h, s.fu, 12 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess ||
+                         cudaMemcpy(s.fd_h, s.fd, 12 * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+      if (ok) missing = prefix + ".fu/.fd (device read-back failed)";
+      ok = false;
+    }
     return s;
   }
 };
@@ -747,7 +760,7 @@ static int resolve(svcb_model* m) {
       for (int d = 0; d < 3 && rb.s2d_r; ++d) {
         s2d_taps(rb.k, rb.dil[d], rb.s2d_r, rb.s2d_ml1[d], rb.s2d_nt1[d]);
         s2d_taps(rb.k, 1, rb.s2d_r, rb.s2d_ml2[d], rb.s2d_nt2[d]);
-        const uint64_t per_tap = 2ull * 160 * 160 / 2;   // fp32-typed elements of one (hi, lo) pair
+        const uint64_t per_tap = (uint64_t)kS2dReplicas * 2ull * 160 * 160 / 2;   // fp32-typed elements of one (hi, lo) pair, all replicas
         rb.c1_s2d[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c1." + std::to_string(d) + ".s2d", per_tap * rb.s2d_nt1[d]));
         rb.c2_s2d[d] = reinterpret_cast<const uint8_t*>(R.get(p + ".c2." + std::to_string(d) + ".s2d", per_tap * rb.s2d_nt2[d]));
       }
@@ -1013,6 +1026,8 @@ int svcb_op_amp_conv_tc(const float* x, float* y, const float* res, const float*
   return launch_amp_conv_tc(q, s);
 }
 
+void svcb_debug_s2d_trace(void* dev_buf) { s2d_set_trace(static_cast<long long*>(dev_buf)); }
+
 size_t svcb_op_amp_s2d_link_scratch_bytes(int32_t B, int32_t C, int32_t L) {
   const int r = C > 0 ? 160 / C : 0;
   if (B <= 0 || L <= 0 || !s2d_link_factor(C) || L % r) return 0;
@@ -1038,7 +1053,13 @@ int svcb_op_amp_s2d_link(const float* x, float* y, const float* res, float* y_ac
   AmpS2dParams q;
   q.B = B; q.C = C; q.L = L; q.K = K; q.Rp = s2d_rows(L, r);
   q.a_hi = b0; q.a_lo = b0 + img;
-  if (y_act) { q.o_hi = b0 + 2 * img; q.o_lo = b0 + 3 * img; q.ea = ea_out; q.ib = ib_out; q.fu = fu; q.fd = fd; }
+  if (y_act) {
+    q.o_hi = b0 + 2 * img; q.o_lo = b0 + 3 * img; q.ea = ea_out; q.ib = ib_out; q.fu = fu; q.fd = fd;
+    SnakeW taps;   // (a unit-test entry point: a synchronous read-back of the 24 taps is fine here)
+    SVCB_CUDA_CHECK(cudaMemcpy(taps.fu_h, fu, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+    SVCB_CUDA_CHECK(cudaMemcpy(taps.fd_h, fd, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+    snake_taps_to(taps, q);
+  }
   q.wpk = static_cast<const uint8_t*>(w_s2d); q.bias = bias; q.res = res; q.y = y;
   s2d_taps(K, dilation, r, q.mlo, q.ntaps);
   SVCB_TRY(launch_amp_s2d_link(q, s));

@@ -138,22 +138,28 @@ size_t p8_image_bytes(int B, int C, int L);
 int p8_rows(int L);
 
 // ----------------------------------------------------------------------------- space-to-depth AMP links (C = 20, 10)
+constexpr int kS2dReplicas = 4;   // copies of each matrix set in the blob (pack.py:S2D_REPLICAS)
 struct AmpS2dParams {
   const void* a_hi = nullptr;   // input S2D image (bf16 hi) [B][20][Rp][8] — SnakeAlias already applied
   const void* a_lo = nullptr;
   void* o_hi = nullptr;         // output S2D image = SnakeAlias_next(result), or null
   void* o_lo = nullptr;
-  const uint8_t* wpk = nullptr; // bf16 [ntaps][2 (hi, lo)][20][160][8]  (pack.py:pack_conv_s2d)
+  const uint8_t* wpk = nullptr; // bf16 [kS2dReplicas][ntaps][2 (hi, lo)][20][160][8]  (pack.py:pack_conv_s2d)
   const float* bias = nullptr;  // [C]
   const float* res = nullptr;   // residual [B, C, L] fp32 or null
   float* y = nullptr;           // fp32 result [B, C, L] or null
   const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;   // Snake of the output image
+  float fu2[12] = {0}, fdn[12] = {0};   // the same taps BY VALUE (fu2 = 2 * up taps: UpSample1d's ratio gain folded,
+                                        // exact): kernel parameters live in the constant bank, so the FIR FMAs
+                                        // take them as operands and no register holds a tap
   int B = 0, C = 0, L = 0, K = 0;   // K = taps of the original conv (bookkeeping only)
   int Rp = 0;                   // image rows per (item, octet) = s2d_rows(L, r)
   int ntaps = 0, mlo = 0;       // Toeplitz row offsets -mlo .. ntaps-1-mlo (pack.py:s2d_taps)
   int accum = 0;                // y = y_old + v
   float out_div = 0.f;          // then / out_div when != 0
+  long long* trace = nullptr;   // debugging: CTA 0 writes clock64() stamps of its first 32 tiles ([tile][16]) or null
 };
+void s2d_set_trace(long long* dev_buf);   // test hook: trace buffer used by the next launches (null = off)
 int launch_amp_s2d_link(const AmpS2dParams& p, cudaStream_t s);
 int launch_snake_pack_s2d(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
                           const float* fd, int B, int C, int L, cudaStream_t s);
