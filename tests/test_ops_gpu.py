@@ -201,7 +201,8 @@ def test_conv_tc_epilogues(ops):
 
 @pytest.mark.parametrize("C,L,K,dil", [(20, 8 * 126 * 2, 3, 1), (20, 8 * 300, 11, 5), (20, 8 * 126, 7, 3), (20, 8 * 5, 11, 3),
                                        (20, 8, 3, 1), (20, 8 * 1000, 11, 1), (10, 16 * 126, 3, 1), (10, 16 * 200, 11, 5),
-                                       (10, 16 * 3, 7, 5), (10, 16 * 257, 7, 1)])
+                                       (10, 16 * 3, 7, 5), (10, 16 * 257, 7, 1), (40, 4 * 124 * 2, 3, 1), (40, 4 * 500, 11, 5),
+                                       (40, 8, 7, 3), (40, 4 * 126, 11, 1), (40, 4 * 1002, 7, 5)])
 def test_amp_s2d_link(ops, sd, C, L, K, dil):
     """One AMP-block link of the narrow stages in space-to-depth form (csrc/amp_s2d.cu): block-Toeplitz
     tcgen05 conv (bf16x3) with bias + residual, and the NEXT SnakeAlias computed in the epilogue — both

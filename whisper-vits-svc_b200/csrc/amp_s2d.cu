@@ -41,7 +41,7 @@ constexpr int PADR = 16;          // zero rows in front of every (item, octet) o
 constexpr int TILE = 128;         // accumulator rows per tile
 constexpr uint32_t A_PART = KC * RA * 16;       // 46,080 B
 constexpr uint32_t W_SLOT = KC * N * 16;        // 51,200 B: one (tap, hi|lo) matrix
-constexpr uint32_t STG_BYTES = 64 + 4 * TILE * 16 * 4 + 64 + 4 * 64 * 4;   // 4 sample strips (+ guards) + 4 edge buffers
+constexpr uint32_t STG_BYTES = 64 + 4 * TILE * 16 * 4 + 64 + 4 * 128 * 4;  // 4 sample strips (+ guards) + 4 edge buffers
 constexpr uint32_t SMEM = 2 * A_PART + 2 * W_SLOT + STG_BYTES;
 constexpr int EPI_WARPS = 16;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
@@ -119,8 +119,7 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
   const int run = blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (run * 8 >= L) return;
-  const int opr = r >> 3;                       // octets per row of this channel
-  const int row = run / opr, o = c * opr + run % opr;
+  const int opr = r >> 3;                       // octets per row of this channel (0 for r = 4: half an octet)
   const float* xr = x + ((long long)b * C + c) * L;
   const int n0 = run * 8;
   const float a_ = __ldg(ea + c), b_ = __ldg(inv_b + c);
@@ -139,14 +138,31 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
     for (int j = 0; j < 24; ++j) xw[j] = __ldg(xr + min(max(n0 - 8 + j, 0), L - 1));
   }
   s2d_snake8(xw, fu, fdn, a_, b_, out, first, last);
-  const long long row_elem = ((((long long)b * s2d::KC + o) * Rp) + s2d::PADR + row) * 8;
-  s2d_store_octet(hi, lo, row_elem, out);
+  if (opr) {
+    const int row = run / opr, o = c * opr + run % opr;
+    const long long row_elem = ((((long long)b * s2d::KC + o) * Rp) + s2d::PADR + row) * 8;
+    s2d_store_octet(hi, lo, row_elem, out);
+  } else {   // r = 4: the run covers rows 2*run, 2*run+1; this channel is half (4 elements) of octet c / 2
+    __align__(8) __nv_bfloat162 h2[4], l2[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      h2[k] = __floats2bfloat162_rn(out[2 * k], out[2 * k + 1]);
+      const float2 f = __bfloat1622float2(h2[k]);
+      l2[k] = __floats2bfloat162_rn(out[2 * k] - f.x, out[2 * k + 1] - f.y);
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      const long long e = ((((long long)b * s2d::KC + (c >> 1)) * Rp) + s2d::PADR + 2 * run + hrow) * 8 + (c & 1) * 4;
+      *reinterpret_cast<uint2*>(hi + e) = *reinterpret_cast<const uint2*>(h2 + 2 * hrow);
+      *reinterpret_cast<uint2*>(lo + e) = *reinterpret_cast<const uint2*>(l2 + 2 * hrow);
+    }
+  }
 }
 
 int launch_snake_pack_s2d(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
                           const float* fd, int B, int C, int L, cudaStream_t s) {
   const int r = C > 0 ? s2d::N / C : 0;
-  if (B <= 0 || L <= 0 || C * r != s2d::N || (r != 8 && r != 16) || L % r || (reinterpret_cast<uintptr_t>(x) & 15)) {
+  if (B <= 0 || L <= 0 || C * r != s2d::N || (r != 4 && r != 8 && r != 16) || L % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) {
     set_error("snake_pack_s2d: unsupported shape");
     return SVCB_E_BAD_SHAPE;
   }
@@ -314,8 +330,11 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
     // ------------------------------------------------------------------------------------ epilogue
     const int q = warp & 3, g = warp >> 2;
     const int row = q * 32 + lane;
+    constexpr int CU = R >= 8 ? R : 8;            // accumulator columns per unit: whole channels, >= one image octet
+    constexpr int NCH = CU / R;                   // channels per unit (2 for R = 4)
+    const int NU = p.C / NCH;
     float* stg_g = Stg + 16 + (size_t)g * (TILE * 16);          // one strip of up to 128 x 16 samples per group
-    float* edge_g = Stg + 16 + 4 * (TILE * 16) + 16 + g * 64;      // [4 warps][lane 0: 5 | lane 31: 5] Snake values
+    float* edge_g = Stg + 16 + 4 * (TILE * 16) + 16 + g * 128;     // [4 warps][<= 2 channels][lane 0: 5 | lane 31: 5] Snake values
     __nv_bfloat16* o_hi = static_cast<__nv_bfloat16*>(p.o_hi);
     __nv_bfloat16* o_lo = static_cast<__nv_bfloat16*>(p.o_lo);
     const bool do_div = p.out_div != 0.f;
@@ -327,15 +346,16 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
       const int tau = tau0 + row;
       const bool valid = tau >= 0 && tau < nrows;
       const bool useful = valid && row >= HS && row < TILE - HS;
-      // residual rows are independent of the accumulator: the first channel's are requested before the
-      // wait, every later channel's one channel ahead (their latency was 19 % of all stall samples)
+      // residual rows are independent of the accumulator: the first unit's are requested before the wait,
+      // every later unit's one unit ahead (their latency was 19 % of all stall samples)
       const bool has_res = p.res != nullptr && valid;
       const long long xrow = (long long)b * p.C * p.L + (long long)tau * R;
-      float4 rcur[R / 4], rnext[R / 4];
-      auto load_res = [&](int c, float4 (&dst)[R / 4]) {
+      float4 rcur[CU / 4], rnext[CU / 4];
+      auto load_res = [&](int u, float4 (&dst)[CU / 4]) {
         if (has_res) {
 #pragma unroll
-          for (int j = 0; j < R / 4; ++j) dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + xrow + (long long)c * p.L) + j);
+          for (int j = 0; j < CU / 4; ++j)
+            dst[j] = __ldg(reinterpret_cast<const float4*>(p.res + xrow + (long long)(u * NCH + j / (R / 4)) * p.L) + j % (R / 4));
         }
       };
       load_res(g, rcur);
@@ -344,62 +364,72 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
       if (warp == 0) S2D_TRACE(11);
       tc::fence_after_sync();
       const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_STRIDE;
-      for (int c = g; c < p.C; c += 4) {
-        if (c + 4 < p.C) load_res(c + 4, rnext);
-        float v[R];
+      for (int u = g; u < NU; u += 4) {                     // unit = one channel (R >= 8) or a channel pair (R = 4)
+        if (u + 4 < NU) load_res(u + 4, rnext);
+        const int c0 = u * NCH;
+        float v[CU];
         {
-          uint32_t u[R];
-          if constexpr (R == 8) tc::tmem_ld8(tbase + (uint32_t)(c * R), u);
-          else tc::tmem_ld16(tbase + (uint32_t)(c * R), u);
+          uint32_t w[CU];
+          if constexpr (CU == 8) tc::tmem_ld8(tbase + (uint32_t)(u * CU), w);
+          else tc::tmem_ld16(tbase + (uint32_t)(u * CU), w);
           tc::tmem_ld_wait();
-          const float bias = __ldg(p.bias + c);
 #pragma unroll
-          for (int j = 0; j < R; ++j) v[j] = __uint_as_float(u[j]) + bias;
+          for (int k = 0; k < NCH; ++k) {
+            const float bias = __ldg(p.bias + c0 + k);
+#pragma unroll
+            for (int j = 0; j < R; ++j) v[k * R + j] = __uint_as_float(w[k * R + j]) + bias;
+          }
         }
-        const long long xoff = xrow + (long long)c * p.L;
         if (has_res) {
 #pragma unroll
-          for (int j = 0; j < R / 4; ++j) {
+          for (int j = 0; j < CU / 4; ++j) {
             v[4 * j] += rcur[j].x; v[4 * j + 1] += rcur[j].y; v[4 * j + 2] += rcur[j].z; v[4 * j + 3] += rcur[j].w;
           }
         }
 #pragma unroll
-        for (int j = 0; j < R / 4; ++j) rcur[j] = rnext[j];
+        for (int j = 0; j < CU / 4; ++j) rcur[j] = rnext[j];
         if (p.y && useful) {
-          float4* yp = reinterpret_cast<float4*>(p.y + xoff);
 #pragma unroll
-          for (int j = 0; j < R / 4; ++j) {
+          for (int j = 0; j < CU / 4; ++j) {
+            float4* yp = reinterpret_cast<float4*>(p.y + xrow + (long long)(c0 + j / (R / 4)) * p.L) + j % (R / 4);
             float4 o4 = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            if (p.accum) { const float4 y4 = yp[j]; o4.x += y4.x; o4.y += y4.y; o4.z += y4.z; o4.w += y4.w; }
+            if (p.accum) { const float4 y4 = *yp; o4.x += y4.x; o4.y += y4.y; o4.z += y4.z; o4.w += y4.w; }
             // a real (uniform) branch: if-converted, the division would run its x/0 slow path per element
             if (do_div) { asm volatile(""); o4.x = o4.x / p.out_div; o4.y = o4.y / p.out_div; o4.z = o4.z / p.out_div; o4.w = o4.w / p.out_div; }
-            yp[j] = o4;
+            *yp = o4;
           }
         }
         if (p.o_hi) {
           // SnakeAlias of the result, written as the next link's operand image.  A row owns R consecutive
-          // samples of the channel: it up-samples + applies Snake to ITS 2R values only (the 4 + 4 samples
-          // it needs from the neighbouring rows come from the shared strip), then the 5 + 5 Snake values of
+          // samples of a channel: it up-samples + applies Snake to ITS 2R values only (the 4 + 4 samples it
+          // needs from the neighbouring rows come from the shared strip), then the 5 + 5 Snake values of
           // the neighbouring rows that its decimation filter reaches arrive by warp shuffle (lanes 0 / 31:
-          // through a 64-float edge buffer), so nothing is computed twice: 30 FMA + 2 sin per sample
-          // instead of 46 + 3.5 for the register-run form with recomputed halos.
-          float* strip = stg_g;
+          // through a small edge buffer), so nothing is computed twice: 30 FMA + 2 sin per sample instead
+          // of 46 + 3.5 for the register-run form with recomputed halos.  Sequence ends: the reference's
+          // replicate padding of x (alias/resample.py:28) and of the 2x signal (alias/filter.py:90-91)
+          // are two selects each — no scalar path.
 #pragma unroll
-          for (int j = 0; j < R / 4; ++j)
-            *reinterpret_cast<float4*>(strip + row * R + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int k = 0; k < NCH; ++k) {
+            float* strip = stg_g + k * (TILE * R);
+#pragma unroll
+            for (int j = 0; j < R / 4; ++j)
+              *reinterpret_cast<float4*>(strip + row * R + 4 * j) =
+                  make_float4(v[k * R + 4 * j], v[k * R + 4 * j + 1], v[k * R + 4 * j + 2], v[k * R + 4 * j + 3]);
+          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-          const float a_ = __ldg(p.ea + c), b_ = __ldg(p.ib + c);
-          float vall[2 * R + 10];                                    // [prev 5 | own 2R | next 5]
-          {
+          float vall[NCH][2 * R + 10];                               // per channel: [prev 5 | own 2R | next 5]
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            const float a_ = __ldg(p.ea + c0 + k), b_ = __ldg(p.ib + c0 + k);
+            const float* strip = stg_g + k * (TILE * R);
             float xw[R + 8];                                         // samples -4 .. R+3 relative to the row's first
             float4 l4 = *reinterpret_cast<const float4*>(strip + row * R - 4);   // (row 0 / 127 read 16 B outside the
             float4 r4 = *reinterpret_cast<const float4*>(strip + row * R + R);   //  strip: halo rows, values unused)
-            // sequence ends: the reference pads x by replication before up-sampling (alias/resample.py:28)
-            if (tau == 0) l4 = make_float4(v[0], v[0], v[0], v[0]);
-            if (tau == nrows - 1) r4 = make_float4(v[R - 1], v[R - 1], v[R - 1], v[R - 1]);
+            if (tau == 0) l4 = make_float4(v[k * R], v[k * R], v[k * R], v[k * R]);
+            if (tau == nrows - 1) r4 = make_float4(v[k * R + R - 1], v[k * R + R - 1], v[k * R + R - 1], v[k * R + R - 1]);
             xw[0] = l4.x; xw[1] = l4.y; xw[2] = l4.z; xw[3] = l4.w;
 #pragma unroll
-            for (int j = 0; j < R; ++j) xw[4 + j] = v[j];
+            for (int j = 0; j < R; ++j) xw[4 + j] = v[k * R + j];
             xw[R + 4] = r4.x; xw[R + 5] = r4.y; xw[R + 6] = r4.z; xw[R + 7] = r4.w;
 #pragma unroll
             for (int a = 0; a < R; ++a) {
@@ -410,55 +440,61 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
               uo = fmaf(xw[a + 3], p.fu2[8], uo); uo = fmaf(xw[a + 4], p.fu2[6], uo); uo = fmaf(xw[a + 5], p.fu2[4], uo);
               uo = fmaf(xw[a + 6], p.fu2[2], uo); uo = fmaf(xw[a + 7], p.fu2[0], uo);
               const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);
-              vall[5 + 2 * a] = fmaf(b_, se * se, ue);
-              vall[5 + 2 * a + 1] = fmaf(b_, so * so, uo);
+              vall[k][5 + 2 * a] = fmaf(b_, se * se, ue);
+              vall[k][5 + 2 * a + 1] = fmaf(b_, so * so, uo);
+            }
+            float* edge = edge_g + (q * NCH + k) * 16;
+            if (lane == 0) {
+#pragma unroll
+              for (int i = 0; i < 5; ++i) edge[i] = vall[k][5 + i];
+            }
+            if (lane == 31) {
+#pragma unroll
+              for (int i = 0; i < 5; ++i) edge[8 + i] = vall[k][2 * R + i];
             }
           }
-          float* edge = edge_g + q * 16;
-          if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) edge[i] = vall[5 + i];
-          }
-          if (lane == 31) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) edge[8 + i] = vall[5 + 2 * R - 5 + i];
-          }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+          float out[CU];
 #pragma unroll
-          for (int i = 0; i < 5; ++i) {
-            vall[i] = __shfl_up_sync(0xffffffffu, vall[2 * R + i], 1);          // previous row's last five
-            vall[2 * R + 5 + i] = __shfl_down_sync(0xffffffffu, vall[5 + i], 1);  // next row's first five
-          }
-          if (lane == 0 && q > 0) {
+          for (int k = 0; k < NCH; ++k) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) vall[i] = edge_g[(q - 1) * 16 + 8 + i];
-          }
-          if (lane == 31 && q < 3) {
+            for (int i = 0; i < 5; ++i) {
+              const float up = __shfl_up_sync(0xffffffffu, vall[k][2 * R + i], 1);      // previous row's last five
+              const float dn = __shfl_down_sync(0xffffffffu, vall[k][5 + i], 1);       // next row's first five
+              vall[k][i] = up;
+              vall[k][2 * R + 5 + i] = dn;
+            }
+            if (lane == 0 && q > 0) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) vall[2 * R + 5 + i] = edge_g[(q + 1) * 16 + i];
-          }
-          // ... and the 2x signal by replication before decimating (alias/filter.py:90-91)
-          if (tau == 0) {
+              for (int i = 0; i < 5; ++i) vall[k][i] = edge_g[((q - 1) * NCH + k) * 16 + 8 + i];
+            }
+            if (lane == 31 && q < 3) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) vall[i] = vall[5];
-          }
-          if (tau == nrows - 1) {
+              for (int i = 0; i < 5; ++i) vall[k][2 * R + 5 + i] = edge_g[((q + 1) * NCH + k) * 16 + i];
+            }
+            if (tau == 0) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) vall[2 * R + 5 + i] = vall[2 * R + 4];
+              for (int i = 0; i < 5; ++i) vall[k][i] = vall[k][5];
+            }
+            if (tau == nrows - 1) {
+#pragma unroll
+              for (int i = 0; i < 5; ++i) vall[k][2 * R + 5 + i] = vall[k][2 * R + 4];
+            }
+#pragma unroll
+            for (int n = 0; n < R; ++n) {                            // out[n] = sum_k V[2n - 5 + k] f[k], V[j] = vall[j + 5]
+              float accd = vall[k][2 * n] * p.fdn[0];
+#pragma unroll
+              for (int t = 1; t < 12; ++t) accd = fmaf(vall[k][2 * n + t], p.fdn[t], accd);
+              out[k * R + n] = accd;
+            }
           }
           if (useful) {
 #pragma unroll
-            for (int h = 0; h < R / 8; ++h) {
+            for (int h = 0; h < CU / 8; ++h) {                       // 8 consecutive K' indices = one image octet row
               float oh[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const int n = 8 * h + i;                            // out[n] = sum_k V[2n - 5 + k] f[k], V[j] = vall[j + 5]
-                float accd = vall[2 * n] * p.fdn[0];
-#pragma unroll
-                for (int k = 1; k < 12; ++k) accd = fmaf(vall[2 * n + k], p.fdn[k], accd);
-                oh[i] = accd;
-              }
-              const int oc = c * (R / 8) + h;
+              for (int i = 0; i < 8; ++i) oh[i] = out[8 * h + i];
+              const int oc = u * (CU / 8) + h;
               const long long row_elem = ((((long long)b * KC + oc) * p.Rp) + PADR + tau) * 8;
               s2d_store_octet(o_hi, o_lo, row_elem, oh);
             }
@@ -483,8 +519,8 @@ int launch_amp_s2d_link(const AmpS2dParams& p_in, cudaStream_t s) {
   AmpS2dParams p = p_in;
   p.trace = g_s2d_trace;
   const int r = p.C > 0 ? s2d::N / p.C : 0;
-  if (p.B <= 0 || p.L <= 0 || p.C * r != s2d::N || (r != 8 && r != 16) || p.L % r) {
-    set_error("amp_s2d_link: unsupported shape (need C * r = 160 with r in {8, 16} and L % r == 0)");
+  if (p.B <= 0 || p.L <= 0 || p.C * r != s2d::N || (r != 4 && r != 8 && r != 16) || p.L % r) {
+    set_error("amp_s2d_link: unsupported shape (need C * r = 160 with r in {4, 8, 16} and L % r == 0)");
     return SVCB_E_BAD_SHAPE;
   }
   if (p.ntaps < 1 || p.mlo < 0 || p.mlo > s2d::A_OFF || p.ntaps - 1 - p.mlo > s2d::RA - s2d::TILE - s2d::A_OFF ||
@@ -492,7 +528,7 @@ int launch_amp_s2d_link(const AmpS2dParams& p_in, cudaStream_t s) {
     set_error("amp_s2d_link: tap range exceeds the A panel, wrong image rows or missing operand");
     return SVCB_E_BAD_SHAPE;
   }
-  static DevSmemCache c8, c16;
+  static DevSmemCache c4, c8, c16;
   const int n_sm = device_sm_count();
   if (n_sm <= 0) { set_error("amp_s2d_link: cannot query the SM count"); return SVCB_E_CUDA; }
   const int S = s2d_tile_stride(r);
@@ -503,7 +539,10 @@ int launch_amp_s2d_link(const AmpS2dParams& p_in, cudaStream_t s) {
   const double el = (double)p.B * p.C * p.L;
   KernelScope ks(kname, s, 2.0 * p.C * p.K * el, el * (4.0 + (p.o_hi ? 4.0 : 0.0) + (p.res ? 4.0 : 0.0) + (p.y ? (p.accum ? 8.0 : 4.0) : 0.0)),
                  p.o_hi ? 70.0 * el : 0.0);
-  if (r == 8) {
+  if (r == 4) {
+    SVCB_CUDA_CHECK(ensure_dyn_smem(amp_s2d_link_kernel<4>, s2d::SMEM, c4));
+    amp_s2d_link_kernel<4><<<grid, s2d::THREADS, s2d::SMEM, s>>>(p);
+  } else if (r == 8) {
     SVCB_CUDA_CHECK(ensure_dyn_smem(amp_s2d_link_kernel<8>, s2d::SMEM, c8));
     amp_s2d_link_kernel<8><<<grid, s2d::THREADS, s2d::SMEM, s>>>(p);
   } else {

@@ -98,7 +98,7 @@ struct ResBlock {
 };
 
 // must match pack.py:S2D_LINK_FACTORS / s2d_taps
-static int s2d_link_factor(int ch) { return ch == 20 ? 8 : ch == 10 ? 16 : 0; }
+static int s2d_link_factor(int ch) { return ch == 40 ? 4 : ch == 20 ? 8 : ch == 10 ? 16 : 0; }
 static void s2d_taps(int k, int dil, int r, int& mlo, int& ntaps) {
   const int P = dil * (k - 1) / 2;
   mlo = (P + r - 1) / r;
@@ -375,7 +375,7 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
   const int prec = m->cfg.precision;
   for (int j = 0; j < nres; ++j) {
     const ResBlock& R = m->res[stage * nres + j];
-    if (prec == 3 && R.s2d_r && S2D[0] && L % R.s2d_r == 0) {
+    if (prec == 3 && R.s2d_r && S2D[0] && L % R.s2d_r == 0 && L % 8 == 0) {
       // narrow stages: every link = block-Toeplitz tcgen05 conv with the next SnakeAlias in its epilogue
       const int Rp = s2d_rows(L, R.s2d_r);
       void *ia_hi = S2D[0], *ia_lo = S2D[1], *ib_hi = S2D[2], *ib_lo = S2D[3];
@@ -597,7 +597,7 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     SVCB_TRY(tap(ctx, SVCB_TAP_GEN_UP0 + i, X, (size_t)B * chn * Ln));
     void* S2D[4] = {nullptr, nullptr, nullptr, nullptr};
     const int s2r = c.precision == 3 ? s2d_link_factor(chn) : 0;
-    if (s2r && Ln % s2r == 0) {
+    if (s2r && Ln % s2r == 0 && Ln % 8 == 0) {
       // two ping-pong S2D images (hi, lo each), cleared once per stage: rows outside the sequences are the
       // convolutions' zero padding and are never written by the link kernels
       const size_t ib = s2d_image_bytes(B, Ln, s2r);
@@ -1040,7 +1040,7 @@ int svcb_op_amp_s2d_link(const float* x, float* y, const float* res, float* y_ac
                          int32_t K, int32_t dilation, void* scratch, size_t scratch_bytes, svcb_stream stream) {
   g_launches = 0;
   const int r = s2d_link_factor(C);
-  if (!r || B <= 0 || L <= 0 || L % r) { set_error("svcb_op_amp_s2d_link: need C in {20, 10} and L % (160/C) == 0"); return SVCB_E_BAD_SHAPE; }
+  if (!r || B <= 0 || L <= 0 || L % r || L % 8) { set_error("svcb_op_amp_s2d_link: need C in {40, 20, 10}, L % (160/C) == 0 and L % 8 == 0"); return SVCB_E_BAD_SHAPE; }
   const size_t img = (s2d_image_bytes(B, L, r) + 255) & ~(size_t)255;
   if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < 4 * img) {
     set_error("svcb_op_amp_s2d_link: scratch too small or misaligned");

@@ -138,7 +138,7 @@ size_t p8_image_bytes(int B, int C, int L);
 int p8_rows(int L);
 
 // ----------------------------------------------------------------------------- space-to-depth AMP links (C = 20, 10)
-constexpr int kS2dReplicas = 4;   // copies of each matrix set in the blob (pack.py:S2D_REPLICAS)
+constexpr int kS2dReplicas = 1;   // copies of each matrix set in the blob (pack.py:S2D_REPLICAS)
 struct AmpS2dParams {
   const void* a_hi = nullptr;   // input S2D image (bf16 hi) [B][20][Rp][8] — SnakeAlias already applied
   const void* a_lo = nullptr;

@@ -64,8 +64,8 @@ def pack_conv_tc(w: torch.Tensor) -> torch.Tensor:
 
 
 S2D_WIDTH = 160   # K' = N' = C * r of the space-to-depth AMP links (csrc/amp_s2d.cu)
-S2D_REPLICAS = 4             # copies of every matrix set in the blob; must match csrc/common.cuh:kS2dReplicas
-S2D_LINK_FACTORS = (8, 16)   # factors csrc/amp_s2d.cu implements (C = 20, 10); must match api.cu:s2d_link_factor
+S2D_REPLICAS = 1             # copies of every matrix set in the blob; must match csrc/common.cuh:kS2dReplicas
+S2D_LINK_FACTORS = (4, 8, 16)   # factors csrc/amp_s2d.cu implements (C = 40, 20, 10); must match api.cu:s2d_link_factor
 
 
 def s2d_factor(c: int) -> int:
@@ -110,10 +110,9 @@ def pack_conv_s2d(w: torch.Tensor, dil: int, r: int) -> torch.Tensor:
     lo = (W - hi.float()).bfloat16()
     st = torch.stack([hi, lo], 1)                              # [T, 2, n, k]
     img = st.view(T, 2, n, k // 8, 8).permute(0, 1, 3, 2, 4).contiguous()   # [T, 2, kc, n, 8]
-    # S2D_REPLICAS identical copies back to back: every CTA of a launch streams the SAME few hundred KB of
-    # matrices per tile, and 148 SMs reading the same L2 lines in lockstep were served at ~3 TB/s only (the
-    # MMA warp waited ~7k cycles per tap for its weights); CTA i reads copy i % S2D_REPLICAS, which spreads
-    # the hot lines over more L2 slices.
+    # S2D_REPLICAS identical copies back to back (CTA i reads copy i % S2D_REPLICAS): a knob for spreading the
+    # hot L2 lines of the matrices every CTA streams per tile.  Measured with 4 copies: no change (the links
+    # are bound by their epilogue, not by weight delivery), so one copy is packed.
     return img.view(torch.float32).reshape(-1).repeat(S2D_REPLICAS)
 
 
