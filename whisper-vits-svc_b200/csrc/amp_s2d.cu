@@ -211,9 +211,15 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t a_full, a_empty, w_full[2], w_empty[2], t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ float s_par[3][40];      // bias | exp(alpha) | 1 / (exp(beta) + 1e-9) of every channel (C <= 40)
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int warp_u = tc::warp_uniform_idx();
+  if (tid < p.C) {
+    s_par[0][tid] = __ldg(p.bias + tid);
+    s_par[1][tid] = p.o_hi ? __ldg(p.ea + tid) : 0.f;
+    s_par[2][tid] = p.o_hi ? __ldg(p.ib + tid) : 0.f;
+  }
   constexpr int HS = R >= 8 ? 1 : 2;
   constexpr int S = TILE - 2 * HS;
   const int nrows = p.L / R;
@@ -364,21 +370,30 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
       if (warp == 0) S2D_TRACE(11);
       tc::fence_after_sync();
       const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_STRIDE;
+      // accumulator columns are fetched one unit ahead (8-column units): the tcgen05.ld of unit u+4 is in
+      // flight while unit u runs its Snake
+      uint32_t wpre[8];
+      if constexpr (CU == 8) tc::tmem_ld8(tbase + (uint32_t)(g * CU), wpre);
       for (int u = g; u < NU; u += 4) {                     // unit = one channel (R >= 8) or a channel pair (R = 4)
         if (u + 4 < NU) load_res(u + 4, rnext);
         const int c0 = u * NCH;
         float v[CU];
-        {
-          uint32_t w[CU];
-          if constexpr (CU == 8) tc::tmem_ld8(tbase + (uint32_t)(u * CU), w);
-          else tc::tmem_ld16(tbase + (uint32_t)(u * CU), w);
-          tc::tmem_ld_wait();
+        if constexpr (CU == 8) {
+          tc::tmem_ld_wait8(wpre);
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            const float bias = __ldg(p.bias + c0 + k);
+            const float bias = s_par[0][c0 + k];
 #pragma unroll
-            for (int j = 0; j < R; ++j) v[k * R + j] = __uint_as_float(w[k * R + j]) + bias;
+            for (int j = 0; j < R; ++j) v[k * R + j] = __uint_as_float(wpre[k * R + j]) + bias;
           }
+          if (u + 4 < NU) tc::tmem_ld8(tbase + (uint32_t)((u + 4) * CU), wpre);
+        } else {
+          uint32_t w[CU];
+          tc::tmem_ld16(tbase + (uint32_t)(u * CU), w);
+          tc::tmem_ld_wait();
+          const float bias = s_par[0][c0];
+#pragma unroll
+          for (int j = 0; j < R; ++j) v[j] = __uint_as_float(w[j]) + bias;
         }
         if (has_res) {
 #pragma unroll
@@ -420,7 +435,7 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
           float vall[NCH][2 * R + 10];                               // per channel: [prev 5 | own 2R | next 5]
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            const float a_ = __ldg(p.ea + c0 + k), b_ = __ldg(p.ib + c0 + k);
+            const float a_ = s_par[1][c0 + k], hb_ = 0.5f * s_par[2][c0 + k];
             const float* strip = stg_g + k * (TILE * R);
             float xw[R + 8];                                         // samples -4 .. R+3 relative to the row's first
             float4 l4 = *reinterpret_cast<const float4*>(strip + row * R - 4);   // (row 0 / 127 read 16 B outside the
@@ -439,9 +454,10 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
               float uo = xw[a + 2] * p.fu2[10];
               uo = fmaf(xw[a + 3], p.fu2[8], uo); uo = fmaf(xw[a + 4], p.fu2[6], uo); uo = fmaf(xw[a + 5], p.fu2[4], uo);
               uo = fmaf(xw[a + 6], p.fu2[2], uo); uo = fmaf(xw[a + 7], p.fu2[0], uo);
-              const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);
-              vall[k][5 + 2 * a] = fmaf(b_, se * se, ue);
-              vall[k][5 + 2 * a + 1] = fmaf(b_, so * so, uo);
+              // u + sin^2(a u) / (e^beta + 1e-9) = (u + b/2) - (b/2) cos(2 a u): one multiply less per value
+              const float ce = snake_cos2(ue * a_), co = snake_cos2(uo * a_);
+              vall[k][5 + 2 * a] = fmaf(-hb_, ce, ue + hb_);
+              vall[k][5 + 2 * a + 1] = fmaf(-hb_, co, uo + hb_);
             }
             float* edge = edge_g + (q * NCH + k) * 16;
             if (lane == 0) {

@@ -84,6 +84,14 @@ __device__ __forceinline__ float snake_sin(float x) {
   return __sinf(r);
 }
 
+// cos(2x) with the same reduction (for sin^2 x = (1 - cos 2x) / 2): x = k pi + r, |r| <= pi/2, cos 2x = cos 2r.
+__device__ __forceinline__ float snake_cos2(float x) {
+  const float k = (fmaf(x, 0.3183098861837907f, 12582912.f)) - 12582912.f;    // rint(x / pi)
+  float r = fmaf(k, -3.140625f, x);                  // pi = 3.140625 (exact in 9 bits) + 9.6765358979e-4
+  r = fmaf(k, -9.676535897932e-4f, r);
+  return __cosf(r + r);
+}
+
 // ----------------------------------------------------------------------------- conv1d
 enum ConvFlags : int {
   CONV_IN_MASK = 1,    // x[b,:,t] treated as 0 for t >= lengths[b]

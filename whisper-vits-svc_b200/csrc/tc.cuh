@@ -114,6 +114,14 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
       : "r"(taddr)
       : "memory");
 }
+// wait::ld that names the destination registers of an earlier tmem_ld8 as in-out operands: the compiler
+// then cannot move a read of them above the wait (needed when the load was issued an iteration earlier)
+__device__ __forceinline__ void tmem_ld_wait8(uint32_t (&v)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7])
+               :
+               : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
