@@ -5,8 +5,9 @@ The reference loads Whisper once, writes a .ppg.npy per file and then starts one
 `python svc_inference.py` subprocess per file (svc_inference_batch.py:34-43), re-loading the SVC
 checkpoint and re-spawning the HuBERT / pitch extractors every time.  Here the model is loaded
 once per GPU, files are sharded across the ranks of a `torchrun` launch (one process per GPU, one
-NCCL broadcast of the packed weights, no collective on the data path) and every file runs
-in-process.  HuBERT / CREPE are outside the B200 hot path: `<name>.vec.npy` and
+NCCL broadcast of the packed weights, no collective on the data path), and per rank the chunks of ALL its
+files are bucketed by length and run as full device batches (hostio.BatchEngine) while host threads read
+features and write WAVs.  HuBERT / CREPE are outside the B200 hot path: `<name>.vec.npy` and
 `<name>.pit.csv` must sit next to `<name>.wav` (or in --feat); a file without them is reported and
 skipped — the reference would silently produce nothing for it either (subprocess exit codes are
 ignored there).
@@ -37,6 +38,7 @@ def main():
     parser.add_argument('--shift', type=int, default=0, help="Pitch shift key.")
     parser.add_argument('--feat', type=str, default=None, help="dir holding <name>.{ppg,vec}.npy / .pit.csv")
     parser.add_argument('--whisper', type=str, default=os.path.join("whisper_pretrain", "large-v2.pt"))
+    parser.add_argument('--max-batch', type=int, default=32, help="chunks per device call (equal-length chunks of all files)")
     args = parser.parse_args()
     wave_path = args.wave
     assert os.path.isdir(wave_path), f"{wave_path} is not folder"
@@ -67,26 +69,52 @@ def main():
     spk = torch.FloatTensor(np.load(args.spk))
     whisper = None
     done, failed = 0, []
-    for i in mine:
+
+    def load(i):
+        """Features of one utterance (host threads: file reads overlap the device batches)."""
         name = waves[i]
         stem = os.path.join(feat, name[:-4])
-        try:
-            ppg_p, vec_p, pit_p = stem + ".ppg.npy", stem + ".vec.npy", stem + ".pit.csv"
-            if not (os.path.isfile(vec_p) and os.path.isfile(pit_p)):
-                raise FileNotFoundError(f"{vec_p} / {pit_p} missing (HuBERT and CREPE extractors are out of scope)")
-            if not os.path.isfile(ppg_p):
+        ppg_p, vec_p, pit_p = stem + ".ppg.npy", stem + ".vec.npy", stem + ".pit.csv"
+        if not (os.path.isfile(vec_p) and os.path.isfile(pit_p)):
+            raise FileNotFoundError(f"{vec_p} / {pit_p} missing (HuBERT and CREPE extractors are out of scope)")
+        if not os.path.isfile(ppg_p):
+            ppg_p = os.path.join(out_path, name + ".ppg.npy")     # written by the PPG pass below
+        ppg, vec, pit = hostio.prepare_features(ppg_p, vec_p, pit_p, args.shift)
+        return name, spk, pit, ppg, vec
+
+    # PPG pass for files that have none yet (one Whisper load per rank; chunks of a file run as one batch)
+    for i in mine:
+        name = waves[i]
+        if not os.path.isfile(os.path.join(feat, name[:-4] + ".ppg.npy")):
+            try:
                 from whisper_vits_svc_b200 import whisper_infer
                 if whisper is None:
                     whisper = whisper_infer.load_model(args.whisper, device)
-                ppg_p = os.path.join(out_path, name + ".ppg.npy")
-                whisper_infer.pred_ppg(whisper, os.path.join(wave_path, name), ppg_p, device)
-            ppg, vec, pit = hostio.prepare_features(ppg_p, vec_p, pit_p, args.shift)
-            audio = hostio.svc_infer(model, spk, pit, ppg, vec, hp, device, write_pit_wav=None)
-            write(os.path.join(out_path, name), hp.data.sampling_rate, audio)
-            done += 1
-        except Exception as e:  # a failed utterance must not stop the shard
-            failed.append((name, repr(e)))
-            print(f"[rank {rank}] {name}: FAILED {e}")
+                whisper_infer.pred_ppg(whisper, os.path.join(wave_path, name), os.path.join(out_path, name + ".ppg.npy"), device)
+            except Exception as e:
+                print(f"[rank {rank}] {name}: PPG extraction FAILED {e}")
+    del whisper
+
+    from concurrent.futures import ThreadPoolExecutor
+    engine = hostio.BatchEngine(model, hp, device, max_batch=args.max_batch)
+    loaders, writers = ThreadPoolExecutor(max_workers=4), ThreadPoolExecutor(max_workers=4)
+
+    def jobs():
+        futs = [loaders.submit(load, i) for i in mine]
+        for i, f in zip(mine, futs):
+            try:
+                yield f.result()
+            except Exception as e:  # a failed utterance must not stop the shard
+                failed.append((waves[i], repr(e)))
+                print(f"[rank {rank}] {waves[i]}: FAILED {e}")
+
+    pending = []
+    for name, audio in engine.run(jobs()):
+        pending.append(writers.submit(write, os.path.join(out_path, name), hp.data.sampling_rate, audio))
+        done += 1
+    for f in pending:
+        f.result()
+    loaders.shutdown(); writers.shutdown()
     total = shard.sum_over_ranks(float(done), device)
     if rank == 0:
         print(f"svc_inference_batch: {int(total)}/{len(waves)} files converted on {world} GPU(s)")

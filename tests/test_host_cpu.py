@@ -136,3 +136,31 @@ def test_bench_reference_arm_contract():
     # the arm times a bounded sample of OUR headline workload: same config record as the GPU arm
     import bench
     assert d["config"] == bench.headline_config(32, 1000, 320000, 1)
+
+
+def test_batch_engine_plan_buckets_equal_length_chunks():
+    """hostio.BatchEngine.plan: every chunk of every utterance exactly once, batches hold equal-length
+    chunks only (SnakeAlias pads by replication at a chunk's true end, so ragged batches would not be
+    reference-exact), at most max_batch per device call, longest first; the pieces reassemble to the
+    reference's output length n*hop - 1 per utterance."""
+    from whisper_vits_svc_b200 import hostio
+    lengths = [1000, 1000, 2600, 37, 1000, 5050, 1, 2500, 2511, 1000]
+    hop, mb = 320, 3
+    chunks, batches = hostio.BatchEngine.plan(lengths, hop, mb)
+    seen = sorted(j for b in batches for j in b)
+    assert seen == list(range(len(chunks)))
+    last = None
+    for b in batches:
+        assert 1 <= len(b) <= mb
+        ns = {chunks[j][2] - chunks[j][1] for j in b}
+        assert len(ns) == 1
+        n = ns.pop()
+        assert last is None or n <= last
+        last = n
+    for u, n in enumerate(lengths):
+        mine = sorted((c for c in chunks if c[0] == u), key=lambda c: c[1])
+        assert [(c[1], c[2], c[3], c[4]) for c in mine] == hostio.chunk_plan(n, hop)
+        # (so, eo) are the reference's slice bounds into the chunk's output (eo may be negative: svc_inference.py:112,129)
+        assert sum(len(range((c[2] - c[1]) * hop)[c[3]:c[4]]) for c in mine) == n * hop - 1
+    # 4 utterances of 1000 frames -> one batch of 3 and one of 1
+    assert sorted(len(b) for b in batches if chunks[b[0]][2] - chunks[b[0]][1] == 1000) == [1, 3]
