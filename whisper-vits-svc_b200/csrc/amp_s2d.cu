@@ -41,9 +41,13 @@ constexpr int PADR = 16;          // zero rows in front of every (item, octet) o
 constexpr int TILE = 128;         // accumulator rows per tile
 constexpr uint32_t A_PART = KC * RA * 16;       // 46,080 B
 constexpr uint32_t W_SLOT = KC * N * 16;        // 51,200 B: one (tap, hi|lo) matrix
-constexpr uint32_t STG_BYTES = 64 + 4 * TILE * 16 * 4 + 64 + 4 * 128 * 4;  // 4 sample strips (+ guards) + 4 edge buffers
+constexpr int GROUPS = 5;                       // epilogue column groups (x 4 TMEM lane quadrants = 20 warps)
+constexpr int STRIP = TILE * 8;                 // floats of one group's strip: 128 rows x (first 4 | last 4 samples) of one channel,
+                                                // or 128 rows x 4 samples of two channels (r = 4)
+constexpr uint32_t STG_BYTES = 64 + GROUPS * STRIP * 4 + 64 + GROUPS * 128 * 4;  // sample strips (+ guards) + edge buffers
 constexpr uint32_t SMEM = 2 * A_PART + 2 * W_SLOT + STG_BYTES;
-constexpr int EPI_WARPS = 16;
+static_assert(SMEM + 1024 <= 227 * 1024, "A panel + weight ring + strips must fit the 227 KB of one CTA");
+constexpr int EPI_WARPS = 4 * GROUPS;
 constexpr int THREADS = (EPI_WARPS + 2) * 32;
 constexpr uint32_t ACC_STRIDE = 256;            // TMEM columns between the two accumulators
 }  // namespace s2d
@@ -201,7 +205,9 @@ int launch_s2d_unpack(const void* hi, const void* lo, float* y, int B, int C, in
 //                  2-slot ring (one 51,200-byte bulk copy each)
 //   MMA warp       per tap: A_hi x W_hi, A_lo x W_hi, A_hi x W_lo — 30 MMAs (N = 160) with compile-time
 //                  descriptor offsets (no per-MMA integer work in the issuing thread)
-//   16 epilogue warps = 4 column groups x 4 TMEM lane quadrants: group g owns channels c = g (mod 4)
+//   20 epilogue warps = 5 column groups x 4 TMEM lane quadrants: group g owns units u = g (mod 5), a unit
+//                  being one channel (r >= 8) or a channel pair (r = 4): 4 / 4 / 2 units per group for
+//                  C = 20 / 40 / 10 — balanced for every stage
 #define S2D_TRACE(slot) do { if (p.trace && blockIdx.x == 0 && it < 32 && lane == 0) p.trace[it * 16 + (slot)] = clock64(); } while (0)
 
 template <int R>
@@ -339,8 +345,8 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
     constexpr int CU = R >= 8 ? R : 8;            // accumulator columns per unit: whole channels, >= one image octet
     constexpr int NCH = CU / R;                   // channels per unit (2 for R = 4)
     const int NU = p.C / NCH;
-    float* stg_g = Stg + 16 + (size_t)g * (TILE * 16);          // one strip of up to 128 x 16 samples per group
-    float* edge_g = Stg + 16 + 4 * (TILE * 16) + 16 + g * 128;     // [4 warps][<= 2 channels][lane 0: 5 | lane 31: 5] Snake values
+    float* stg_g = Stg + 16 + (size_t)g * STRIP;                     // this group's strip (see the staging comment below)
+    float* edge_g = Stg + 16 + GROUPS * STRIP + 16 + g * 128;        // [4 warps][<= 2 channels][lane 0: 5 | lane 31: 5] Snake values
     __nv_bfloat16* o_hi = static_cast<__nv_bfloat16*>(p.o_hi);
     __nv_bfloat16* o_lo = static_cast<__nv_bfloat16*>(p.o_lo);
     const bool do_div = p.out_div != 0.f;
@@ -374,8 +380,8 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
       // flight while unit u runs its Snake
       uint32_t wpre[8];
       if constexpr (CU == 8) tc::tmem_ld8(tbase + (uint32_t)(g * CU), wpre);
-      for (int u = g; u < NU; u += 4) {                     // unit = one channel (R >= 8) or a channel pair (R = 4)
-        if (u + 4 < NU) load_res(u + 4, rnext);
+      for (int u = g; u < NU; u += GROUPS) {                     // unit = one channel (R >= 8) or a channel pair (R = 4)
+        if (u + GROUPS < NU) load_res(u + GROUPS, rnext);
         const int c0 = u * NCH;
         float v[CU];
         if constexpr (CU == 8) {
@@ -386,7 +392,7 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
 #pragma unroll
             for (int j = 0; j < R; ++j) v[k * R + j] = __uint_as_float(wpre[k * R + j]) + bias;
           }
-          if (u + 4 < NU) tc::tmem_ld8(tbase + (uint32_t)((u + 4) * CU), wpre);
+          if (u + GROUPS < NU) tc::tmem_ld8(tbase + (uint32_t)((u + GROUPS) * CU), wpre);
         } else {
           uint32_t w[CU];
           tc::tmem_ld16(tbase + (uint32_t)(u * CU), w);
@@ -423,23 +429,26 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
           // of 46 + 3.5 for the register-run form with recomputed halos.  Sequence ends: the reference's
           // replicate padding of x (alias/resample.py:28) and of the 2x signal (alias/filter.py:90-91)
           // are two selects each — no scalar path.
+          // strip layout per channel: [row][first 4 samples | last 4 samples] (for R = 4 both are the row's
+          // 4 samples) — all a neighbouring row ever reads
+          constexpr int RS = R == 4 ? 4 : 8;                         // strip floats per row and channel
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            float* strip = stg_g + k * (TILE * R);
-#pragma unroll
-            for (int j = 0; j < R / 4; ++j)
-              *reinterpret_cast<float4*>(strip + row * R + 4 * j) =
-                  make_float4(v[k * R + 4 * j], v[k * R + 4 * j + 1], v[k * R + 4 * j + 2], v[k * R + 4 * j + 3]);
+            float* strip = stg_g + k * (TILE * RS);
+            *reinterpret_cast<float4*>(strip + row * RS) = make_float4(v[k * R], v[k * R + 1], v[k * R + 2], v[k * R + 3]);
+            if constexpr (R > 4)
+              *reinterpret_cast<float4*>(strip + row * RS + 4) =
+                  make_float4(v[k * R + R - 4], v[k * R + R - 3], v[k * R + R - 2], v[k * R + R - 1]);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           float vall[NCH][2 * R + 10];                               // per channel: [prev 5 | own 2R | next 5]
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
             const float a_ = s_par[1][c0 + k], hb_ = 0.5f * s_par[2][c0 + k];
-            const float* strip = stg_g + k * (TILE * R);
+            const float* strip = stg_g + k * (TILE * RS);
             float xw[R + 8];                                         // samples -4 .. R+3 relative to the row's first
-            float4 l4 = *reinterpret_cast<const float4*>(strip + row * R - 4);   // (row 0 / 127 read 16 B outside the
-            float4 r4 = *reinterpret_cast<const float4*>(strip + row * R + R);   //  strip: halo rows, values unused)
+            float4 l4 = *reinterpret_cast<const float4*>(strip + row * RS - 4);    // previous row's last four (row 0 / 127
+            float4 r4 = *reinterpret_cast<const float4*>(strip + row * RS + RS);   //  read outside the strip: halo rows, unused)
             if (tau == 0) l4 = make_float4(v[k * R], v[k * R], v[k * R], v[k * R]);
             if (tau == nrows - 1) r4 = make_float4(v[k * R + R - 1], v[k * R + R - 1], v[k * R + R - 1], v[k * R + R - 1]);
             xw[0] = l4.x; xw[1] = l4.y; xw[2] = l4.z; xw[3] = l4.w;
