@@ -226,6 +226,14 @@ int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float*
                           const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
                           int32_t window, int32_t T, svcb_stream stream);
 
+/* The same attention on the tensor cores (csrc/rel_attn_tc.cu; what the pipeline runs in precision 1 / 3): q.k^T
+ * and p.v as tcgen05 MMAs over bf16 hi/lo split operands, fp32 softmax; head dim 96 and window 4 only.
+ * scratch >= svcb_op_rel_attention_tc_scratch_bytes(B, heads, T), 256-byte aligned. */
+size_t svcb_op_rel_attention_tc_scratch_bytes(int32_t B, int32_t heads, int32_t T);
+int svcb_op_rel_attention_tc(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
+                             const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
+                             int32_t window, int32_t T, void* scratch, size_t scratch_bytes, svcb_stream stream);
+
 /* General stride-1 "same" Conv1d on the tensor cores (csrc/conv_tc.cu): x [B,Cin,T] fp32,
  * w_tc = pack.py:pack_conv_tc_general image, y [B,Cout,T] ([B,Cout/2,T] with the gate flag).
  * flags: 1 input mask, 2 output mask (need lengths), 4 WaveNet gate on interleaved channel pairs,

@@ -99,6 +99,8 @@ SIGNATURES = {
     "svcb_op_snake_alias": (c_int, [c_void_p] * 6 + [c_int32] * 3 + [c_void_p]),
     "svcb_op_layernorm_c": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_float, c_void_p]),
     "svcb_op_rel_attention": (c_int, [c_void_p] * 5 + [c_int32] * 5 + [c_void_p]),
+    "svcb_op_rel_attention_tc_scratch_bytes": (c_size_t, [c_int32] * 3),
+    "svcb_op_rel_attention_tc": (c_int, [c_void_p] * 5 + [c_int32] * 5 + [c_void_p, c_size_t, c_void_p]),
     "svcb_op_conv_tc": (c_int, [c_void_p] * 6 + [c_int32] * 9 + [c_void_p]),
     "svcb_op_amp_conv_tc_scratch_bytes": (c_size_t, [c_int32] * 3),
     "svcb_op_amp_conv_tc": (c_int, [c_void_p] * 9 + [c_int32] * 6 + [c_void_p, c_size_t, c_void_p]),

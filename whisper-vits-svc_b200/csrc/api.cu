@@ -57,7 +57,7 @@ struct ConvW {
 
 // must match pack.py:tc_tiling
 static void tc_tiling(ConvW& w) {
-  w.kch = (w.cin % 64 == 0) ? 64 : 32;
+  w.kch = 32;   // (64 when cin % 64 == 0 was the round-1 choice: one CTA per SM for the 192-channel convs)
   w.cin_pad = (w.cin + w.kch - 1) / w.kch * w.kch;
   const int cp16 = (w.cout + 15) / 16 * 16;
   w.ntiles = (cp16 + 255) / 256;
@@ -284,6 +284,9 @@ static int run_prior(const svcb_model* m, Ctx& ctx, const float* ppg, const floa
   float* att = ctx.alloc<float>((size_t)B * H * T);
   float* hbuf = ctx.alloc<float>((size_t)B * Fc * T);
   float* stats = ctx.alloc<float>((size_t)B * 2 * C * T);
+  const bool attn_tc = c.precision != 0 && H / c.enc_heads == 96 && c.enc_window == 4;
+  const size_t attn_ws_bytes = attn_tc ? rel_attention_ws_bytes(B, c.enc_heads, T) : 0;
+  uint8_t* attn_ws = attn_tc ? ctx.alloc<uint8_t>(attn_ws_bytes) : nullptr;
   SVCB_TRY(check_ws(ctx));
   {  // pre / hub on time-major inputs (vits/models.py:40-46)
     ConvParams p = std_conv(m->pre, ppg, x, B, T, T, 2);
@@ -301,7 +304,8 @@ static int run_prior(const svcb_model* m, Ctx& ctx, const float* ppg, const floa
   for (int i = 0; i < c.enc_layers; ++i) {
     const EncLayer& L = m->enc[i];
     RUN(run_conv(m, L.qkv, std_conv(L.qkv, x, qkv, B, T, T, 0), s));
-    RUN(launch_rel_attention(qkv, L.ek, L.ev, lengths, att, B, H, c.enc_heads, c.enc_window, T, s));
+    if (attn_tc) RUN(launch_rel_attention_tc(qkv, L.ek, L.ev, lengths, att, attn_ws, attn_ws_bytes, B, H, c.enc_heads, c.enc_window, T, s));
+    else RUN(launch_rel_attention(qkv, L.ek, L.ev, lengths, att, B, H, c.enc_heads, c.enc_window, T, s));
     RUN(run_conv(m, L.o, std_conv(L.o, att, y, B, T, T, 0), s));
     RUN(launch_layernorm_c(x, y, L.ln1g, L.ln1b, x, B, H, T, 0, 1e-5f, s));
     const int pl = (c.enc_kernel - 1) / 2;
@@ -1080,6 +1084,18 @@ int svcb_op_layernorm_c(const float* x, const float* r, const float* gamma, cons
   g_launches = 0;
   return launch_layernorm_c(x, r, gamma, beta, y, B, C, T, gb_batch_stride, eps,
                             static_cast<cudaStream_t>(stream));
+}
+
+size_t svcb_op_rel_attention_tc_scratch_bytes(int32_t B, int32_t heads, int32_t T) {
+  return (B > 0 && heads > 0 && T > 0) ? rel_attention_ws_bytes(B, heads, T) : 0;
+}
+
+int svcb_op_rel_attention_tc(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,
+                             const int64_t* lengths, float* out, int32_t B, int32_t H, int32_t heads,
+                             int32_t window, int32_t T, void* scratch, size_t scratch_bytes, svcb_stream stream) {
+  g_launches = 0;
+  return launch_rel_attention_tc(qkv, emb_rel_k, emb_rel_v, reinterpret_cast<const long long*>(lengths), out, scratch,
+                                 scratch_bytes, B, H, heads, window, T, static_cast<cudaStream_t>(stream));
 }
 
 int svcb_op_rel_attention(const float* qkv, const float* emb_rel_k, const float* emb_rel_v,

@@ -233,6 +233,10 @@ int launch_snake_alias(const float* x, float* y, const float* ea, const float* i
 int launch_layernorm_c(const float* x, const float* r, const float* gamma, const float* beta,
                        float* y, int B, int C, int T, int gb_batch_stride, float eps,
                        cudaStream_t s);
+// tensor-core form (csrc/rel_attn_tc.cu): bf16x3 split operands, scratch = rel_attention_ws_bytes()
+size_t rel_attention_ws_bytes(int B, int heads, int T);
+int launch_rel_attention_tc(const float* qkv, const float* ek, const float* ev, const long long* lengths, float* out,
+                            void* ws, size_t ws_bytes, int B, int H, int heads, int window, int T, cudaStream_t s);
 int launch_rel_attention(const float* qkv, const float* ek, const float* ev,
                          const long long* lengths, float* out, int B, int H, int heads, int window,
                          int T, cudaStream_t s);

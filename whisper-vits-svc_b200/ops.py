@@ -60,13 +60,20 @@ def layernorm_c(x, r, gamma, beta, eps=1e-5):
     return y
 
 
-def rel_attention(qkv, emb_k, emb_v, lengths, heads=2, window=4):
+def rel_attention(qkv, emb_k, emb_v, lengths, heads=2, window=4, tc=False):
     qkv = _c(qkv)
     B, H3, T = qkv.shape
     H = H3 // 3
     ek, ev = _c(emb_k.reshape(2 * window + 1, -1)), _c(emb_v.reshape(2 * window + 1, -1))
     lengths = lengths.to(qkv.device, torch.int64).contiguous()
     out = torch.empty(B, H, T, device=qkv.device)
+    if tc:
+        lib = _lib.load()
+        scratch = torch.empty(int(lib.svcb_op_rel_attention_tc_scratch_bytes(B, heads, T)), dtype=torch.uint8, device=qkv.device)
+        st = lib.svcb_op_rel_attention_tc(qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), lengths.data_ptr(), out.data_ptr(),
+                                          B, H, heads, window, T, scratch.data_ptr(), scratch.numel(), _s())
+        _lib.check(st, "svcb_op_rel_attention_tc")
+        return out
     st = _lib.load().svcb_op_rel_attention(qkv.data_ptr(), ek.data_ptr(), ev.data_ptr(), lengths.data_ptr(),
                                            out.data_ptr(), B, H, heads, window, T, _s())
     _lib.check(st, "svcb_op_rel_attention")

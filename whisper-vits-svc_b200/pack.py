@@ -116,9 +116,12 @@ def pack_conv_s2d(w: torch.Tensor, dil: int, r: int) -> torch.Tensor:
     return img.view(torch.float32).reshape(-1).repeat(S2D_REPLICAS)
 
 
+TC_KCH64 = False   # input-channel chunk of csrc/conv_tc.cu: 32 everywhere lets two CTAs share an SM (api.cu:tc_tiling)
+
+
 def tc_tiling(cout: int, cin: int):
     """(kch, cin_pad, bn, ntiles) — must match csrc/api.cu:tc_tiling."""
-    kch = 64 if cin % 64 == 0 else 32
+    kch = 64 if (cin % 64 == 0 and TC_KCH64) else 32
     cin_pad = (cin + kch - 1) // kch * kch
     cp16 = (cout + 15) // 16 * 16
     ntiles = (cp16 + 255) // 256
