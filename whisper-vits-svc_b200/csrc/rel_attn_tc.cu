@@ -36,9 +36,10 @@ constexpr uint32_t P_PART = (TK / 8) * TQ * 16, P_BYTES = 2 * P_PART;    // 32,7
 constexpr uint32_t E_PART = KCD * 16 * 16, E_BYTES = 2 * E_PART;         // 6,144 (Ek padded to 16 rows)
 constexpr uint32_t OFF_Q = 0, OFF_K = OFF_Q + Q_TILE, OFF_V = OFF_K + 2 * K_TILE, OFF_P = OFF_V + 2 * V_TILE,
                    OFF_E = OFF_P + P_BYTES, OFF_QE = OFF_E + E_BYTES, OFF_PB = OFF_QE + TQ * 12 * 4,
-                   OFF_EV = OFF_PB + TQ * 12 * 4, SMEM = OFF_EV + NREL * D * 4;
+                   OFF_EV = OFF_PB + TQ * 12 * 4, OFF_ML = OFF_EV + NREL * D * 4, SMEM = OFF_ML + 2 * TQ * 2 * 4;
 constexpr uint32_t COL_S = 0, COL_QE = 128, COL_O = 160, TMEM_COLS = 256;
-constexpr int THREADS = 192;
+constexpr int SM_WARPS = 8;          // softmax warps: two per TMEM lane quadrant, 32 of the 64 key columns each
+constexpr int THREADS = (SM_WARPS + 2) * 32;
 }  // namespace ra
 
 size_t rel_attention_ws_bytes(int B, int heads, int T) {
@@ -153,24 +154,24 @@ rel_attn_tc_kernel(const uint8_t* __restrict__ qimg, const uint8_t* __restrict__
   for (int i = tid; i < NREL * D; i += THREADS) ev_s[i] = __ldg(ev + i);
   for (int i = tid; i < TQ * 12; i += THREADS) pb_s[i] = 0.f;
   if (tid == 0) {
-    tc::mbar_init(&q_full, 1); tc::mbar_init(&qe_full, 1); tc::mbar_init(&p_full, 128); tc::mbar_init(&p_empty, 1);
+    tc::mbar_init(&q_full, 1); tc::mbar_init(&qe_full, 1); tc::mbar_init(&p_full, SM_WARPS * 32); tc::mbar_init(&p_empty, 1);
     tc::mbar_init(&o_full, 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&k_full[i], 1); tc::mbar_init(&k_empty[i], 1); tc::mbar_init(&v_full[i], 1); tc::mbar_init(&v_empty[i], 1);
-      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], 128);
+      tc::mbar_init(&s_full[i], 1); tc::mbar_init(&s_empty[i], SM_WARPS * 32);
     }
     tc::fence_barrier_init();
   }
   tc::fence_proxy_async_smem();     // the Ek panels were written through the generic proxy
   __syncwarp();
-  if (warp == 4) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
+  if (warp == SM_WARPS) tc::tmem_alloc(&tmem_slot, TMEM_COLS);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const int ntile = 2 * nk;          // key tiles visited: pass 1 then pass 2
 
-  if (warp_u == 4) {
+  if (warp_u == SM_WARPS) {
     // ------------------------------------------------------------------------------------ producer
     if (tc::elect_one()) {
       tc::mbar_arrive_expect_tx(&q_full, Q_TILE);
@@ -188,7 +189,7 @@ rel_attn_tc_kernel(const uint8_t* __restrict__ qimg, const uint8_t* __restrict__
         }
       }
     }
-  } else if (warp_u == 5) {
+  } else if (warp_u == SM_WARPS + 1) {
     // ------------------------------------------------------------------------------------ MMA issuer
     const uint32_t sb = tc::smem_u32(smem);
     const uint64_t dq = tc::smem_desc(sb + OFF_Q, TQ * 16);
@@ -234,105 +235,115 @@ rel_attn_tc_kernel(const uint8_t* __restrict__ qimg, const uint8_t* __restrict__
       }
     }
   } else {
-    // ------------------------------------------------------------------------------------ softmax (warps 0-3)
-    const int row = tid;                       // query row of the tile = TMEM lane
+    // ------------------------------------------------------------------------------------ softmax (warps 0-7)
+    // thread = (query row, half): warps w and w+4 share TMEM lane quadrant w & 3; half = 32 of the 64 key columns
+    const int row = tid & (TQ - 1), half = tid >> 7;
     const int gi = qt * TQ + row;
     const long long len = lengths ? lengths[b] : (long long)T;
     const bool row_masked = gi >= len;
-    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    const uint32_t lane_base = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* ml_s = reinterpret_cast<float*>(smem + OFF_ML);   // [2 halves][128][m, l]
     tc::mbar_wait_parked(&qe_full, 0);
     tc::fence_after_sync();
-    {
+    if (half == 0) {
       uint32_t u[16];
       tc::tmem_ld16(lane_base + COL_QE, u);
       tc::tmem_ld_wait();
 #pragma unroll
       for (int r = 0; r < NREL; ++r) qe_s[row * 12 + r] = __uint_as_float(u[r]);
     }
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // qe_s of the row is read by both halves
     float m = -1e30f, l = 0.f, inv_l = 0.f;
     for (int i = 0; i < ntile; ++i) {
       const bool pass2 = i >= nk;
       const int kt = pass2 ? i - nk : i, buf = i & 1;
-      if (i == nk) inv_l = 1.f / l;
+      if (i == nk) {   // combine the two halves' (max, sum) of pass 1
+        ml_s[(half * TQ + row) * 2] = m; ml_s[(half * TQ + row) * 2 + 1] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        const float mo = ml_s[((half ^ 1) * TQ + row) * 2], lo_ = ml_s[((half ^ 1) * TQ + row) * 2 + 1];
+        const float mn = fmaxf(m, mo);
+        l = l * __expf(m - mn) + lo_ * __expf(mo - mn);
+        m = mn;
+        inv_l = 1.f / l;
+      }
       tc::mbar_wait_parked(&s_full[buf], (uint32_t)((i >> 1) & 1));
       tc::fence_after_sync();
-      if (pass2 && kt >= 1) tc::mbar_wait_parked(&p_empty, (uint32_t)((kt - 1) & 1));   // P of tile kt-1 consumed
-      const int j0 = kt * TK;
-      const int dlo = j0 - gi + W;             // band index of column 0: r = dlo + jj
-      const bool band = dlo + TK - 1 >= 0 && dlo < NREL;
+      const int j0 = kt * TK + half * 32;      // first key column of this thread's half
+      const int dlo = j0 - gi + W;             // band index of that column: r = dlo + jj
+      const bool band = dlo + 31 >= 0 && dlo < NREL;
+      uint32_t u[32];
+      tc::tmem_ld16(lane_base + COL_S + (uint32_t)(buf * TK + half * 32), reinterpret_cast<uint32_t(&)[16]>(u[0]));
+      tc::tmem_ld16(lane_base + COL_S + (uint32_t)(buf * TK + half * 32 + 16), reinterpret_cast<uint32_t(&)[16]>(u[16]));
+      tc::tmem_ld_wait();
+      float sc[32];
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        uint32_t u[32];
-        tc::tmem_ld16(lane_base + COL_S + (uint32_t)(buf * TK + half * 32), reinterpret_cast<uint32_t(&)[16]>(u[0]));
-        tc::tmem_ld16(lane_base + COL_S + (uint32_t)(buf * TK + half * 32 + 16), reinterpret_cast<uint32_t(&)[16]>(u[16]));
-        tc::tmem_ld_wait();
-        float s[32];
-#pragma unroll
-        for (int jj = 0; jj < 32; ++jj) {
-          const int j = j0 + half * 32 + jj;
-          float sv = __uint_as_float(u[jj]);
-          if (band) {
-            const int r = dlo + half * 32 + jj;
-            if ((unsigned)r < (unsigned)NREL) sv += qe_s[row * 12 + r];
-          }
-          if (row_masked || j >= len) sv = -1e4f;
-          if (j >= T) sv = -INFINITY;
-          s[jj] = sv;
+      for (int jj = 0; jj < 32; ++jj) {
+        const int j = j0 + jj;
+        float sv = __uint_as_float(u[jj]);
+        if (band) {
+          const int r = dlo + jj;
+          if ((unsigned)r < (unsigned)NREL) sv += qe_s[row * 12 + r];
         }
-        if (!pass2) {
-          float mx = s[0];
-#pragma unroll
-          for (int jj = 1; jj < 32; ++jj) mx = fmaxf(mx, s[jj]);
-          const float m_new = fmaxf(m, mx);
-          float sum = 0.f;
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) sum += __expf(s[jj] - m_new);
-          l = l * __expf(m - m_new) + sum;
-          m = m_new;
-        } else {
-#pragma unroll
-          for (int oc = 0; oc < 4; ++oc) {     // 4 octets of 8 keys = the K-chunks of the P operand
-            float p8[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) p8[e] = __expf(s[oc * 8 + e] - m) * inv_l;
-            if (band) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const int r = dlo + half * 32 + oc * 8 + e;
-                if ((unsigned)r < (unsigned)NREL) pb_s[row * 12 + r] = p8[e];
-              }
-            }
-            uint4 hi, lo;
-            ra_split8(p8, hi, lo);
-            const int kc = half * 4 + oc;
-            *reinterpret_cast<uint4*>(smem + OFF_P + (size_t)(kc * TQ + row) * 16) = hi;
-            *reinterpret_cast<uint4*>(smem + OFF_P + P_PART + (size_t)(kc * TQ + row) * 16) = lo;
-          }
-        }
+        if (row_masked || j >= len) sv = -1e4f;
+        if (j >= T) sv = -INFINITY;
+        sc[jj] = sv;
       }
+      // the accumulator is in registers now: hand it back before the arithmetic
       tc::fence_before_sync();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&s_empty[buf])) : "memory");
-      if (pass2) {
+      if (!pass2) {
+        float mx = sc[0];
+#pragma unroll
+        for (int jj = 1; jj < 32; ++jj) mx = fmaxf(mx, sc[jj]);
+        const float m_new = fmaxf(m, mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) sum += __expf(sc[jj] - m_new);
+        l = l * __expf(m - m_new) + sum;
+        m = m_new;
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) sc[jj] = __expf(sc[jj] - m) * inv_l;
+        if (band) {
+#pragma unroll
+          for (int jj = 0; jj < 32; ++jj) {
+            const int r = dlo + jj;
+            if ((unsigned)r < (unsigned)NREL) pb_s[row * 12 + r] = sc[jj];
+          }
+        }
+        if (kt >= 1) tc::mbar_wait_parked(&p_empty, (uint32_t)((kt - 1) & 1));   // P of tile kt-1 consumed by its MMAs
+#pragma unroll
+        for (int oc = 0; oc < 4; ++oc) {       // 4 octets of 8 keys = K-chunks of the P operand
+          float p8[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) p8[e] = sc[oc * 8 + e];
+          uint4 hi, lo;
+          ra_split8(p8, hi, lo);
+          const int kc = half * 4 + oc;
+          *reinterpret_cast<uint4*>(smem + OFF_P + (size_t)(kc * TQ + row) * 16) = hi;
+          *reinterpret_cast<uint4*>(smem + OFF_P + P_PART + (size_t)(kc * TQ + row) * 16) = lo;
+        }
         tc::fence_proxy_async_smem();          // P panels: generic-proxy stores -> visible to the MMA (async proxy)
         asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&p_full)) : "memory");
       }
     }
-    // epilogue: O (+ relative-value band) -> out[b, h*96 + c, t]
+    // epilogue: O (+ relative-value band) -> out[b, h*96 + c, t]; each half writes 48 of the 96 head dims
     tc::mbar_wait_parked(&o_full, 0);
     tc::fence_after_sync();
+    asm volatile("bar.sync 1, 256;" ::: "memory");          // pb_s entries were written by either half
     float pb[NREL];
 #pragma unroll
     for (int r = 0; r < NREL; ++r) pb[r] = pb_s[row * 12 + r];
     float* ob = out + ((long long)b * H + (long long)h * D) * T + gi;
 #pragma unroll
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      uint32_t u[32];
-      tc::tmem_ld16(lane_base + COL_O + (uint32_t)c0, reinterpret_cast<uint32_t(&)[16]>(u[0]));
-      tc::tmem_ld16(lane_base + COL_O + (uint32_t)(c0 + 16), reinterpret_cast<uint32_t(&)[16]>(u[16]));
+    for (int cc = 0; cc < 3; ++cc) {
+      const int c0 = half * 48 + cc * 16;
+      uint32_t u[16];
+      tc::tmem_ld16(lane_base + COL_O + (uint32_t)c0, u);
       tc::tmem_ld_wait();
       if (gi < T) {
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
+        for (int c = 0; c < 16; ++c) {
           float o = __uint_as_float(u[c]);
 #pragma unroll
           for (int r = 0; r < NREL; ++r) o = fmaf(pb[r], ev_s[r * D + c0 + c], o);
@@ -343,7 +354,7 @@ rel_attn_tc_kernel(const uint8_t* __restrict__ qimg, const uint8_t* __restrict__
   }
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 4) tc::tmem_dealloc(tmem, ra::TMEM_COLS);
+  if (warp == ra::SM_WARPS) tc::tmem_dealloc(tmem, ra::TMEM_COLS);
 }
 
 int launch_rel_attention_tc(const float* qkv, const float* ek, const float* ev, const long long* lengths, float* out,
