@@ -180,13 +180,24 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
 //   MMA warp         all taps x split parts of tile i into TMEM accumulator (i & 1); one elected lane
 //                    issues (tc::elect_one) inside warp-uniform control flow
 //   8 epilogue warps tile i-1: tcgen05.ld -> +bias (+res, +stage accumulation, /3) -> coalesced stores
-struct AmpPlan { int resident, nabuf, acc_stride, ncols, ncat; size_t smem; };
+struct AmpPlan { int resident, nabuf, acc_stride, ncols, ncat, nw; size_t smem; };
+constexpr int AMP_WMAX = 8;   // deepest weight ring
+
+// NK MMAs of one (tap, split part, A part) group: the operands' descriptor low words advance by
+// kk * kstep with kk a compile-time constant.
+template <int NK>
+__device__ __forceinline__ void amp_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                          uint32_t idesc, uint32_t kstep_a, uint32_t kstep_b, uint32_t first_acc) {
+  tc::mma_bf16_lohi(d_tmem, a_lo, a_hi, b_lo, b_hi, idesc, first_acc);
+#pragma unroll
+  for (int kk = 1; kk < NK; ++kk) tc::mma_bf16_lohi(d_tmem, a_lo + kk * kstep_a, a_hi, b_lo + kk * kstep_b, b_hi, idesc, 1u);
+}
 
 __global__ void __launch_bounds__(320, 1)
-amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, const int acc_stride,
+amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, const int nw, const int acc_stride,
                    const uint32_t ncols, const int ncat) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[2], w_empty[2], w_res, t_full[2], t_empty[2];
+  __shared__ __align__(8) uint64_t a_full[2], a_empty[2], w_full[AMP_WMAX], w_empty[AMP_WMAX], w_res, t_full[2], t_empty[2];
   __shared__ uint32_t tmem_slot;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -207,9 +218,9 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&a_full[i], 1); tc::mbar_init(&a_empty[i], 1);
-      tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1);
       tc::mbar_init(&t_full[i], 1); tc::mbar_init(&t_empty[i], 256);
     }
+    for (int i = 0; i < AMP_WMAX; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     tc::mbar_init(&w_res, 1);
     tc::fence_barrier_init();
   }
@@ -258,15 +269,15 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
       }
       if (!resident && ncat) {
         for (int tap = 0; tap < p.K; ++tap, ++wi) {
-          const int st = wi & 1;
-          if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          const int st = wi % nw;
+          if (wi >= nw) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi / nw) - 1) & 1));
           tc::mbar_arrive_expect_tx(&w_full[st], 2 * wb);
           load_tap_cat(Wbase + (size_t)st * 2 * wb, tap, &w_full[st]);
         }
       } else if (!resident) {
         for (int i = 0; i < nch; ++i, ++wi) {
-          const int st = wi & 1;
-          if (wi >= 2) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi >> 1) - 1) & 1));
+          const int st = wi % nw;
+          if (wi >= nw) tc::mbar_wait(&w_empty[st], (uint32_t)(((wi / nw) - 1) & 1));
           tc::mbar_arrive_expect_tx(&w_full[st], wb);
           tc::bulk_g2s(Wbase + (size_t)st * wb, p.wpk + ((size_t)(i / parts) * 2 + (i % parts)) * wb, wb, &w_full[st]);
         }
@@ -307,8 +318,8 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
           if (resident) {
             wbase = w0 + (uint32_t)tap * 2u * wb;
           } else {
-            st = wi & 1;
-            tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+            st = wi % nw;
+            tc::mbar_wait(&w_full[st], (uint32_t)((wi / nw) & 1));
             tc::fence_after_sync();
             wbase = w0 + (uint32_t)st * 2u * wb;
           }
@@ -343,24 +354,36 @@ amp_conv_tc_kernel(const AmpConvParams p, const int resident, const int nabuf, c
           if (resident) {
             wbase = w0 + (uint32_t)i * wb;
           } else {
-            st = wi & 1;
-            tc::mbar_wait(&w_full[st], (uint32_t)((wi >> 1) & 1));
+            st = wi % nw;
+            tc::mbar_wait(&w_full[st], (uint32_t)((wi / nw) & 1));
             tc::fence_after_sync();
             wbase = w0 + (uint32_t)st * wb;
           }
           const uint64_t bd0 = tc::smem_desc(wbase, lbo_b);
           const int n_a = (part == 0 && parts == 2) ? 2 : 1;  // Wh meets Ah and Al; Wl meets Ah
+          // descriptor low words of this group, computed in uniform code; the unrolled issue below adds
+          // compile-time multiples of the K steps only (the per-MMA `ad += kstep` of round 1 lived in a vector
+          // register inside the elected branch: IMAD + R2UR per operand per MMA, ~110 cycles per MMA where
+          // the instruction itself needs 52 at N = 80 — profiles/r02_mma_probe.txt)
+          const uint32_t a_hiw = (uint32_t)(ad_hi0 >> 32), b_hiw = (uint32_t)(bd0 >> 32);
+          const uint32_t a0w = (uint32_t)ad_hi0 + tap_off, a1w = (uint32_t)ad_lo0 + tap_off, bw = (uint32_t)bd0;
           if (tc::elect_one()) {
-            uint32_t acc_flag = accumulate;
-            const uint32_t a_hiw = (uint32_t)(ad_hi0 >> 32), b_hiw = (uint32_t)(bd0 >> 32);
-            for (int ap = 0; ap < n_a; ++ap) {
-              uint32_t ad = (uint32_t)(ap == 0 ? ad_hi0 : ad_lo0) + tap_off;   // low words: start-address field
-              uint32_t bd = (uint32_t)bd0;
-              for (int kk = 0; kk < nk; ++kk) {
-                tc::mma_bf16_lohi(d_tmem, ad, a_hiw, bd, b_hiw, idesc, acc_flag);
-                acc_flag = 1;
-                ad += kstep_a;
-                bd += kstep_b;
+            if (nk == 5) {
+              amp_issue<5>(d_tmem, a0w, a_hiw, bw, b_hiw, idesc, kstep_a, kstep_b, accumulate);
+              if (n_a == 2) amp_issue<5>(d_tmem, a1w, a_hiw, bw, b_hiw, idesc, kstep_a, kstep_b, 1u);
+            } else if (nk == 10) {
+              amp_issue<10>(d_tmem, a0w, a_hiw, bw, b_hiw, idesc, kstep_a, kstep_b, accumulate);
+              if (n_a == 2) amp_issue<10>(d_tmem, a1w, a_hiw, bw, b_hiw, idesc, kstep_a, kstep_b, 1u);
+            } else {
+              uint32_t acc_flag = accumulate;
+              for (int ap = 0; ap < n_a; ++ap) {
+                uint32_t ad = ap == 0 ? a0w : a1w, bd = bw;
+                for (int kk = 0; kk < nk; ++kk) {
+                  tc::mma_bf16_lohi(d_tmem, ad, a_hiw, bd, b_hiw, idesc, acc_flag);
+                  acc_flag = 1;
+                  ad += kstep_a;
+                  bd += kstep_b;
+                }
               }
             }
             if (!resident) tc::mma_commit(&w_empty[st]);
@@ -461,9 +484,18 @@ static AmpPlan amp_plan(int Cp, int K, int dil, int nsplit) {
   pl.ncols = (int)tc_cols_host(2 * pl.acc_stride);
   // Measured (r01): resident weights + 2 A buffers (one CTA per SM) beat streaming weights with two
   // CTAs per SM on the C=40/80 stages (33.0 vs 37.1 ms per step), so residency is preferred.
+  pl.nw = 2;
   if (2 * a_buf + nch * wb + 128 <= limit) { pl.resident = 1; pl.nabuf = 2; pl.smem = 2 * a_buf + nch * wb + 128; }
-  else if (2 * a_buf + 2 * wslot + 128 <= limit) { pl.resident = 0; pl.nabuf = 2; pl.smem = 2 * a_buf + 2 * wslot + 128; }
-  else { pl.resident = 0; pl.nabuf = 1; pl.smem = a_buf + 2 * wslot + 128; }
+  else {
+    // streaming weights.  A deeper ring (up to AMP_WMAX slots) was measured for C = 80 (8 x 12.8 KB instead of
+    // 2): no change — these launches are not waiting for weights (nor for the issue loop: the unrolled
+    // amp_issue<> path changed nothing either); their 23.5k cycles per tile against 8.6k of MMAs sit in the
+    // epilogue's residual-load / store round trips.  Two slots are kept.
+    pl.resident = 0;
+    pl.nabuf = (2 * a_buf + 2 * wslot + 128 <= limit) ? 2 : 1;
+    pl.nw = 2;
+    pl.smem = pl.nabuf * a_buf + pl.nw * wslot + 128;
+  }
   return pl;
 }
 
@@ -494,7 +526,7 @@ int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s) {
   snprintf(kname, sizeof(kname), "amp_conv_tc_%s_c%dk%d", p.nsplit == 3 ? "bf16x3" : "bf16", p.C, p.K);
   KernelScope ks(kname, s, 2.0 * macs,
                  (double)p.B * p.C * p.L * ((p.nsplit == 3 ? 4.0 : 2.0) + 4.0 * (p.res ? 2 : 1)));
-  amp_conv_tc_kernel<<<grid, 320, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.acc_stride, (uint32_t)pl.ncols, pl.ncat);
+  amp_conv_tc_kernel<<<grid, 320, pl.smem, s>>>(p, pl.resident, pl.nabuf, pl.nw, pl.acc_stride, (uint32_t)pl.ncols, pl.ncat);
   SVCB_LAUNCH_CHECK("amp_conv_tc");
   return SVCB_OK;
 }
