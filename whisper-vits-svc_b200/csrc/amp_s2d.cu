@@ -441,7 +441,11 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
                   make_float4(v[k * R + R - 4], v[k * R + R - 3], v[k * R + R - 2], v[k * R + R - 1]);
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-          float vall[NCH][2 * R + 10];                               // per channel: [prev 5 | own 2R | next 5]
+          // 2x-rate Snake values as (even, odd) pairs V[a + 3], a = position relative to the row's first sample:
+          // own a = 0 .. R-1; the previous row's last five values are V[0].y, V[1], V[2], the next row's first five
+          // V[R+3], V[R+4], V[R+5].x.  All FIR / range-reduction arithmetic runs as packed f32x2 FMAs (FFMA2 /
+          // FMUL2 / FADD2: one issue slot for the even and the odd phase), taps as uniform-register pairs.
+          float2 V[NCH][R + 6];
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
             const float a_ = s_par[1][c0 + k], hb_ = 0.5f * s_par[2][c0 + k];
@@ -455,62 +459,80 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
 #pragma unroll
             for (int j = 0; j < R; ++j) xw[4 + j] = v[k * R + j];
             xw[R + 4] = r4.x; xw[R + 5] = r4.y; xw[R + 6] = r4.z; xw[R + 7] = r4.w;
+            // consecutive-sample pairs in both alignments, each held in its own (aligned) register pair so that
+            // every FIR step is one FFMA2: XE[m] = (x[2m], x[2m+1]), XO[m] = (x[2m+1], x[2m+2])  (x = xw)
+            float2 XE[(R + 8) / 2], XO[(R + 6) / 2];
+#pragma unroll
+            for (int m2 = 0; m2 < (R + 8) / 2; ++m2) XE[m2] = make_float2(xw[2 * m2], xw[2 * m2 + 1]);
+#pragma unroll
+            for (int m2 = 0; m2 < (R + 6) / 2; ++m2) XO[m2] = make_float2(xw[2 * m2 + 1], xw[2 * m2 + 2]);
 #pragma unroll
             for (int a = 0; a < R; ++a) {
-              float ue = xw[a + 1] * p.fu2[11];
-              ue = fmaf(xw[a + 2], p.fu2[9], ue); ue = fmaf(xw[a + 3], p.fu2[7], ue); ue = fmaf(xw[a + 4], p.fu2[5], ue);
-              ue = fmaf(xw[a + 5], p.fu2[3], ue); ue = fmaf(xw[a + 6], p.fu2[1], ue);
-              float uo = xw[a + 2] * p.fu2[10];
-              uo = fmaf(xw[a + 3], p.fu2[8], uo); uo = fmaf(xw[a + 4], p.fu2[6], uo); uo = fmaf(xw[a + 5], p.fu2[4], uo);
-              uo = fmaf(xw[a + 6], p.fu2[2], uo); uo = fmaf(xw[a + 7], p.fu2[0], uo);
-              // u + sin^2(a u) / (e^beta + 1e-9) = (u + b/2) - (b/2) cos(2 a u): one multiply less per value
-              const float ce = snake_cos2(ue * a_), co = snake_cos2(uo * a_);
-              vall[k][5 + 2 * a] = fmaf(-hb_, ce, ue + hb_);
-              vall[k][5 + 2 * a + 1] = fmaf(-hb_, co, uo + hb_);
+              // (u_even, u_odd)[a] = sum_i (x[a+1+i], x[a+2+i]) * (f[11-2i], f[10-2i])
+              float2 U;
+#pragma unroll
+              for (int i = 0; i < 6; ++i) {
+                const int j = a + 1 + i;
+                const float2 pr = (j & 1) ? XO[(j - 1) / 2] : XE[j / 2];
+                U = i == 0 ? __fmul2_rn(pr, p.fup[0]) : __ffma2_rn(pr, p.fup[i], U);
+              }
+              // u + sin^2(a u) / (e^beta + 1e-9) = (u + b/2) - (b/2) cos(2 a u); a u = k pi + r, |r| <= pi/2
+              const float2 t = __fmul2_rn(U, make_float2(a_, a_));
+              const float2 kq = __fadd2_rn(__ffma2_rn(t, make_float2(0.3183098861837907f, 0.3183098861837907f),
+                                                      make_float2(12582912.f, 12582912.f)),
+                                           make_float2(-12582912.f, -12582912.f));
+              float2 rr = __ffma2_rn(kq, make_float2(-3.140625f, -3.140625f), t);
+              rr = __ffma2_rn(kq, make_float2(-9.676535897932e-4f, -9.676535897932e-4f), rr);
+              rr = __fadd2_rn(rr, rr);
+              const float2 cs = make_float2(__cosf(rr.x), __cosf(rr.y));
+              V[k][a + 3] = __ffma2_rn(make_float2(-hb_, -hb_), cs, __fadd2_rn(U, make_float2(hb_, hb_)));
             }
             float* edge = edge_g + (q * NCH + k) * 16;
             if (lane == 0) {
-#pragma unroll
-              for (int i = 0; i < 5; ++i) edge[i] = vall[k][5 + i];
+              edge[0] = V[k][3].x; edge[1] = V[k][3].y; edge[2] = V[k][4].x; edge[3] = V[k][4].y; edge[4] = V[k][5].x;
             }
             if (lane == 31) {
-#pragma unroll
-              for (int i = 0; i < 5; ++i) edge[8 + i] = vall[k][2 * R + i];
+              edge[8] = V[k][R].y; edge[9] = V[k][R + 1].x; edge[10] = V[k][R + 1].y; edge[11] = V[k][R + 2].x; edge[12] = V[k][R + 2].y;
             }
           }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
           float out[CU];
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) {
-              const float up = __shfl_up_sync(0xffffffffu, vall[k][2 * R + i], 1);      // previous row's last five
-              const float dn = __shfl_down_sync(0xffffffffu, vall[k][5 + i], 1);       // next row's first five
-              vall[k][i] = up;
-              vall[k][2 * R + 5 + i] = dn;
-            }
+            float pv[5], nx[5];                                     // previous row's last five, next row's first five
+            pv[0] = __shfl_up_sync(0xffffffffu, V[k][R].y, 1);     pv[1] = __shfl_up_sync(0xffffffffu, V[k][R + 1].x, 1);
+            pv[2] = __shfl_up_sync(0xffffffffu, V[k][R + 1].y, 1); pv[3] = __shfl_up_sync(0xffffffffu, V[k][R + 2].x, 1);
+            pv[4] = __shfl_up_sync(0xffffffffu, V[k][R + 2].y, 1);
+            nx[0] = __shfl_down_sync(0xffffffffu, V[k][3].x, 1);   nx[1] = __shfl_down_sync(0xffffffffu, V[k][3].y, 1);
+            nx[2] = __shfl_down_sync(0xffffffffu, V[k][4].x, 1);   nx[3] = __shfl_down_sync(0xffffffffu, V[k][4].y, 1);
+            nx[4] = __shfl_down_sync(0xffffffffu, V[k][5].x, 1);
             if (lane == 0 && q > 0) {
 #pragma unroll
-              for (int i = 0; i < 5; ++i) vall[k][i] = edge_g[((q - 1) * NCH + k) * 16 + 8 + i];
+              for (int i = 0; i < 5; ++i) pv[i] = edge_g[((q - 1) * NCH + k) * 16 + 8 + i];
             }
             if (lane == 31 && q < 3) {
 #pragma unroll
-              for (int i = 0; i < 5; ++i) vall[k][2 * R + 5 + i] = edge_g[((q + 1) * NCH + k) * 16 + i];
+              for (int i = 0; i < 5; ++i) nx[i] = edge_g[((q + 1) * NCH + k) * 16 + i];
             }
-            if (tau == 0) {
+            if (tau == 0) {               // the 2x signal is replicate-padded before decimation (alias/filter.py:90-91)
 #pragma unroll
-              for (int i = 0; i < 5; ++i) vall[k][i] = vall[k][5];
+              for (int i = 0; i < 5; ++i) pv[i] = V[k][3].x;
             }
             if (tau == nrows - 1) {
 #pragma unroll
-              for (int i = 0; i < 5; ++i) vall[k][2 * R + 5 + i] = vall[k][2 * R + 4];
+              for (int i = 0; i < 5; ++i) nx[i] = V[k][R + 2].y;
             }
+            V[k][0] = make_float2(0.f, pv[0]); V[k][1] = make_float2(pv[1], pv[2]); V[k][2] = make_float2(pv[3], pv[4]);
+            V[k][R + 3] = make_float2(nx[0], nx[1]); V[k][R + 4] = make_float2(nx[2], nx[3]); V[k][R + 5] = make_float2(nx[4], 0.f);
 #pragma unroll
-            for (int n = 0; n < R; ++n) {                            // out[n] = sum_k V[2n - 5 + k] f[k], V[j] = vall[j + 5]
-              float accd = vall[k][2 * n] * p.fdn[0];
+            for (int n = 0; n < R; ++n) {
+              // out[n] = v[2n-5] f0 + sum_i (v[2n-4+2i], v[2n-3+2i]) . (f[2i+1], f[2i+2]) + v[2n+6] f11
+              float2 acc2 = __fmul2_rn(V[k][n + 1], p.fdp[0]);
 #pragma unroll
-              for (int t = 1; t < 12; ++t) accd = fmaf(vall[k][2 * n + t], p.fdn[t], accd);
-              out[k * R + n] = accd;
+              for (int i = 1; i < 5; ++i) acc2 = __ffma2_rn(V[k][n + 1 + i], p.fdp[i], acc2);
+              float o1 = acc2.x + acc2.y;
+              o1 = fmaf(V[k][n].y, p.fd0, o1);
+              out[k * R + n] = fmaf(V[k][n + 6].x, p.fd11, o1);
             }
           }
           if (useful) {

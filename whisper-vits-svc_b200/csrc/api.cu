@@ -69,6 +69,9 @@ struct SnakeW {
 };
 static void snake_taps_to(const SnakeW& w, AmpS2dParams& q) {
   for (int k = 0; k < 12; ++k) { q.fu2[k] = 2.f * w.fu_h[k]; q.fdn[k] = w.fd_h[k]; }
+  for (int i = 0; i < 6; ++i) q.fup[i] = make_float2(q.fu2[11 - 2 * i], q.fu2[10 - 2 * i]);
+  for (int i = 0; i < 5; ++i) q.fdp[i] = make_float2(q.fdn[2 * i + 1], q.fdn[2 * i + 2]);
+  q.fd0 = q.fdn[0]; q.fd11 = q.fdn[11];
 }
 
 struct EncLayer {

@@ -157,6 +157,8 @@ struct AmpS2dParams {
   const float* res = nullptr;   // residual [B, C, L] fp32 or null
   float* y = nullptr;           // fp32 result [B, C, L] or null
   const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;   // Snake of the output image
+  float2 fup[6] = {}, fdp[5] = {};      // ... as pairs for the packed f32x2 FIRs: fup[i] = (fu2[11-2i], fu2[10-2i]),
+  float fd0 = 0.f, fd11 = 0.f;          //     fdp[i] = (fdn[2i+1], fdn[2i+2]); the two end taps of the decimator apart
   float fu2[12] = {0}, fdn[12] = {0};   // the same taps BY VALUE (fu2 = 2 * up taps: UpSample1d's ratio gain folded,
                                         // exact): kernel parameters live in the constant bank, so the FIR FMAs
                                         // take them as operands and no register holds a tap
