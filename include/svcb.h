@@ -190,6 +190,13 @@ int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias,
 /* softmax(q k^T / sqrt(64)) v per head: qkv bf16 [B*T, 3*D] rows (q|k|v), out bf16 [B*T, D]. */
 int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
                            svcb_stream stream);
+/* The same attention as the encoder runs it (csrc/whisper_attn_tc.cu): q k^T and p v as tcgen05 MMAs with S and
+ * O in tensor memory, operands taken from the head-major layout the QKV GEMM writes (built here from the row-major input).
+ * v_layout: 0 = the V panel read as an MN-major operand with LBO = 128 B between 8-key groups (what the encoder
+ * uses), 1 = LBO / SBO exchanged (kept for the descriptor unit test).  scratch: 256-byte aligned. */
+size_t svcb_op_attention_tc_bf16_scratch_bytes(int32_t B, int32_t T, int32_t D);
+int svcb_op_attention_tc_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
+                              int32_t v_layout, void* scratch, size_t scratch_bytes, svcb_stream stream);
 
 /* Per-kernel timing for roofline reports: after svcb_timing_enable(1) every launch is bracketed
  * by CUDA events on its stream; after the caller synchronises, svcb_timing_report() returns

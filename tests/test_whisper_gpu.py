@@ -76,6 +76,34 @@ def test_attention_bf16(B, T, heads):
     assert max_abs(out.float(), ref) <= 2e-2
 
 
+@pytest.mark.parametrize("B,T,heads,v_layout", [(2, 100, 2, 0), (1, 64, 4, 0), (2, 1500, 2, 0), (1, 333, 20, 0), (3, 129, 4, 0),
+                                                (2, 100, 2, 1)])
+def test_attention_tc_bf16(B, T, heads, v_layout):
+    """The encoder's attention kernel (tcgen05: S and O in tensor memory, V read as an MN-major operand) on its
+    own, fed through the same tile image the QKV GEMM writes.  v_layout 1 exchanges LBO / SBO of the V
+    descriptor: it must NOT match (pins the descriptor semantics the kernel relies on)."""
+    from whisper_vits_svc_b200 import _lib
+    D = heads * 64
+    g = torch.Generator().manual_seed(T + heads)
+    qkv = torch.randn(B, T, 3 * D, generator=g).bfloat16()
+    q, k, v = [t.float().view(B, T, heads, 64).permute(0, 2, 1, 3) for t in qkv.split(D, dim=-1)]
+    ref = (F.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1) @ v).permute(0, 2, 1, 3).reshape(B, T, D)
+    qd = qkv.cuda()
+    out = torch.zeros(B, T, D, device="cuda", dtype=torch.bfloat16)
+    lib = _lib.load()
+    scratch = torch.empty(int(lib.svcb_op_attention_tc_bf16_scratch_bytes(B, T, D)), dtype=torch.uint8, device="cuda")
+    st = lib.svcb_op_attention_tc_bf16(qd.data_ptr(), out.data_ptr(), B, T, D, heads, v_layout, scratch.data_ptr(),
+                                       scratch.numel(), _s())
+    _lib.check(st, "svcb_op_attention_tc_bf16")
+    torch.cuda.synchronize()
+    err = max_abs(out.float(), ref)
+    print(f"attention_tc B={B} T={T} heads={heads} v_layout={v_layout}: max-abs {err:.3e}")
+    if v_layout == 0:
+        assert err <= 2e-2
+    else:
+        assert err > 2e-2
+
+
 @pytest.mark.parametrize("state,heads,layers,B,n", [(256, 4, 4, 2, 200), (512, 8, 4, 1, 301), (1280, 20, 4, 1, 400)])
 def test_encoder_vs_oracle(state, heads, layers, B, n):
     from whisper_vits_svc_b200 import whisper_infer

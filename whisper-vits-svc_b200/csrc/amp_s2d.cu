@@ -561,6 +561,7 @@ amp_s2d_link_kernel(const AmpS2dParams p) {
 
 static long long* g_s2d_trace = nullptr;
 void s2d_set_trace(long long* dev_buf) { g_s2d_trace = dev_buf; }
+long long* s2d_get_trace() { return g_s2d_trace; }
 
 int launch_amp_s2d_link(const AmpS2dParams& p_in, cudaStream_t s) {
   AmpS2dParams p = p_in;

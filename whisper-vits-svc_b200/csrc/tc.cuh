@@ -168,6 +168,33 @@ __device__ __forceinline__ void mma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, ui
       : "memory");
 }
 
+// A operand in tensor memory (lane = row, 32-bit column c holds K elements 2c, 2c+1; K = 16 -> 8 columns), B from
+// shared memory: no shared-memory read of A, so the MMA takes N/2 cycles instead of 32 + N/4 (profiles/r02_mma_probe.txt)
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 16 registers per thread -> 32 lanes x 16 consecutive 32-bit columns (thread i <-> lane base+i)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // One lane of a fully active warp (the same lane every time for the same mask).  Used as
 // `if (elect_one()) { tcgen05.mma ...; tcgen05.commit ... }` inside WARP-UNIFORM control flow
 // (branch on warp_uniform_idx()): descriptors and loop state then live in uniform registers and the

@@ -17,6 +17,9 @@ int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int 
 int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
                              cudaStream_t s);
 int launch_rowmajor_to_image(const void* src, void* dst, int R, int K, int rows, cudaStream_t s);
+int launch_image_to_rowmajor(const void* src, void* dst, int R, int K, cudaStream_t s);
+int launch_qkv_rowmajor_to_heads(const void* src, void* dst, int B, int T, int D, cudaStream_t s);
+int launch_whisper_attention_tc(const void* qkv_img, void* out_img, int B, int T, int D, int heads, int vswap, cudaStream_t s);
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
                    cudaStream_t s);
 struct WBlock {
@@ -50,7 +53,8 @@ static WLayout whisper_layout(const svcb_whisper_config& c, int B, int n) {
   L.x = off; off = align256(off + (size_t)L.M * D * 4);
   const size_t Mp = (size_t)(L.M + 127) / 128 * 128;  // tile images are padded to whole 128-row tiles
   L.a = off; off = align256(off + Mp * D * 2);
-  L.qkv = off; off = align256(off + (size_t)L.M * 3 * D * 2);
+  // QKV in the attention kernel's head-major layout (common.cuh qkv_heads_off): items padded to 128 positions
+  L.qkv = off; off = align256(off + (size_t)B * qkv_heads_tp(L.n2) * 3 * D * 2);
   L.att = off; off = align256(off + Mp * D * 2);
   L.mid = off; off = align256(off + Mp * 4 * D * 2);
   L.total = off + 4096;
@@ -147,11 +151,13 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
   // [D, 3D] weight image; the fp32 CUDA-core version of this layer was 25 % of the encoder's time
   SVCB_TRY(launch_im2col_s2_image(h1, mid, B, D, n, n2, s));
   SVCB_TRY(launch_gemm_tc(mid, w->conv2_wimg, w->conv2_b, x, w->pos, M, D, 3 * D, 3, s, n2));
+  // pad positions of the head-major QKV buffer are read (times P = 0) but never written: keep them finite
+  if (qkv_heads_tp(n2) != n2) SVCB_CUDA_CHECK(cudaMemsetAsync(qkv, 0, (size_t)B * qkv_heads_tp(n2) * 3 * D * 2, s));
   for (int i = 0; i < c.n_layer; ++i) {
     const WBlock& b = w->blocks[i];
     SVCB_TRY(launch_ln_rows(x, b.ln1g, b.ln1b, a, M, D, true, s));
-    SVCB_TRY(launch_gemm_tc(a, b.wqkv, b.bqkv, qkv, nullptr, M, 3 * D, D, 0, s));
-    SVCB_TRY(launch_whisper_attention(qkv, att, B, n2, D, c.n_head, 1, s));
+    SVCB_TRY(launch_gemm_tc(a, b.wqkv, b.bqkv, qkv, nullptr, M, 3 * D, D, 4, s, n2));
+    SVCB_TRY(launch_whisper_attention_tc(qkv, att, B, n2, D, c.n_head, 0, s));
     SVCB_TRY(launch_gemm_tc(att, b.wo, b.bo, x, x, M, D, D, 2, s));
     SVCB_TRY(launch_ln_rows(x, b.ln2g, b.ln2b, a, M, D, true, s));
     SVCB_TRY(launch_gemm_tc(a, b.w1, b.b1, mid, nullptr, M, 4 * D, D, 1, s));
@@ -185,6 +191,30 @@ int svcb_op_gemm_bf16(const void* A_bf16, const void* W_bf16, const float* bias,
   SVCB_TRY(launch_rowmajor_to_image(A_bf16, a_img, M, K, 128, s));
   SVCB_TRY(launch_rowmajor_to_image(W_bf16, w_img, N, K, 256, s));
   return launch_gemm_tc(a_img, w_img, bias, out, res, M, N, K, epilogue, s);
+}
+
+size_t svcb_op_attention_tc_bf16_scratch_bytes(int32_t B, int32_t T, int32_t D) {
+  if (B <= 0 || T <= 0 || D <= 0) return 0;
+  const size_t Mp = ((size_t)B * T + 127) / 128 * 128;
+  return align256((size_t)B * qkv_heads_tp(T) * 3 * D * 2) + align256(Mp * D * 2) + 512;
+}
+
+int svcb_op_attention_tc_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,
+                              int32_t v_layout, void* scratch, size_t scratch_bytes, svcb_stream stream) {
+  // row-major q|k|v in, converted to the GEMM tile image the encoder produces; result converted back
+  if (!scratch || ((uintptr_t)scratch & 255) || scratch_bytes < svcb_op_attention_tc_bf16_scratch_bytes(B, T, D)) {
+    set_error("attention_tc scratch too small or misaligned");
+    return SVCB_E_WORKSPACE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t M = (size_t)B * T;
+  char* qimg = static_cast<char*>(scratch);
+  const size_t qbytes = (size_t)B * qkv_heads_tp(T) * 3 * D * 2;
+  char* oimg = qimg + align256(qbytes);
+  SVCB_CUDA_CHECK(cudaMemsetAsync(qimg, 0, qbytes, s));
+  SVCB_TRY(launch_qkv_rowmajor_to_heads(qkv_bf16, qimg, B, T, D, s));
+  SVCB_TRY(launch_whisper_attention_tc(qimg, oimg, B, T, D, heads, v_layout, s));
+  return launch_image_to_rowmajor(oimg, out_bf16, (int)M, D, s);
 }
 
 int svcb_op_attention_bf16(const void* qkv_bf16, void* out_bf16, int32_t B, int32_t T, int32_t D, int32_t heads,

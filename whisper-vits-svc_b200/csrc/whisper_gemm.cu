@@ -25,7 +25,9 @@ namespace svcb {
 
 // 3: fp32 out = GELU(acc + bias) + res[m % res_mod] — the stem's second convolution as a GEMM over an
 // im2col image, with the positional embedding (period n_ctx rows) as the addend (whisper/model.py:150-157)
-enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3 };
+// 4: bf16 out = acc + bias in the head-major QKV layout of the attention kernel (common.cuh qkv_heads_off;
+//    N = 3 D, rows are items of res_mod positions each; pad rows are zeroed by the caller once)
+enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3, EPI_QKV_HEADS = 4 };
 
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 
@@ -145,7 +147,15 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
               if (EPI == EPI_GELU_BF16_IMAGE) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
               h[j] = __float2bfloat16_rn(x);
             }
-            if (EPI == EPI_GELU_BF16_IMAGE) {  // A operand of the next GEMM (its K = this N)
+            if (EPI == EPI_QKV_HEADS) {   // res_mod = positions per item; 16 columns = two octets of one head
+              __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+              const int Dm = N / 3, n = n0 + c0;
+              const int w = n / Dm, hd = (n - w * Dm) >> 6, d = n & 63;
+              const int bi = m / res_mod, t = m - bi * res_mod;
+              const size_t o = qkv_heads_off(bi, w, hd, t, d, Dm >> 6, qkv_heads_tp(res_mod));
+              *reinterpret_cast<uint4*>(ob + o) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(ob + o + (w != 2 ? 1024 : 512)) = *reinterpret_cast<const uint4*>(h + 8);
+            } else if (EPI == EPI_GELU_BF16_IMAGE) {  // A operand of the next GEMM
               __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
               *reinterpret_cast<uint4*>(ob + img_off(m, n0 + c0, N / GM_BK)) = *reinterpret_cast<const uint4*>(h);
               *reinterpret_cast<uint4*>(ob + img_off(m, n0 + c0 + 8, N / GM_BK)) = *reinterpret_cast<const uint4*>(h + 8);
@@ -194,6 +204,9 @@ int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void
     case EPI_BF16_ROWMAJOR: return launch_gemm_t<256, EPI_BF16_ROWMAJOR>(A, W, bias, out, res, M, N, K, 0, s);
     case EPI_GELU_BF16_IMAGE: return launch_gemm_t<256, EPI_GELU_BF16_IMAGE>(A, W, bias, out, res, M, N, K, 0, s);
     case EPI_RESID_F32: return launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, 0, s);
+    case EPI_QKV_HEADS:
+      if (res_mod <= 0 || M % res_mod || N % 192) { set_error("gemm_tc: epilogue 4 needs rows = items x res_mod, N = 3 x heads x 64"); return SVCB_E_BAD_SHAPE; }
+      return launch_gemm_t<256, EPI_QKV_HEADS>(A, W, bias, out, res, M, N, K, res_mod, s);
     case EPI_GELU_ADD_F32:
       if (!res) { set_error("gemm_tc: epilogue 3 needs the addend"); return SVCB_E_BAD_SHAPE; }
       return launch_gemm_t<256, EPI_GELU_ADD_F32>(A, W, bias, out, res, M, N, K, res_mod, s);
