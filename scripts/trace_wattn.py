@@ -21,6 +21,5 @@ for rep in range(3):
     print("op ms (with image conversions)", e0.elapsed_time(e1))
 lib.svcb_debug_s2d_trace(None)
 t = buf.cpu().tolist()
-print("softmax: wait s_full p1 %d p2 %d | wait p_empty %d | busy p1 %d p2 %d | tmem ld %d | total %d" % (t[0], t[1], t[2], t[3], t[4], t[5], t[6]))
-print("mma: wait K %d s_empty %d p_full %d V %d p1_done %d | total %d" % (t[8], t[9], t[10], t[11], t[12], t[13]))
-print("producer: wait empty %d total %d" % (t[16], t[17]))
+print("softmax: wait s_full %d | busy %d | rescale rounds %d | total %d" % (t[0], t[1], t[3], t[6]))
+print("mma: wait K %d p_full %d V %d | total %d" % (t[8], t[9], t[10], t[13]))

@@ -171,12 +171,12 @@ struct AmpS2dParams {
 };
 // Head-major QKV layout the Whisper attention kernel reads (written by the QKV GEMM's epilogue 4): per item
 // b, per w in {q, k, v}, per head h one block of Tp x 64 bf16 (Tp = T rounded up to 128 rows, pad rows zero);
-// q and k blocks are [Tp/128][8 octets][128 rows][8], v blocks [Tp/64][8 octets][64 rows][8] — every operand
+// q blocks are [Tp/128][8 octets][128 rows][8], k and v blocks [Tp/64][8 octets][64 rows][8] — every operand
 // tile of the attention MMAs is one contiguous SWIZZLE_NONE panel (K-major for q, k; MN-major for v).
 __host__ __device__ inline int qkv_heads_tp(int T) { return (T + 127) / 128 * 128; }
 __host__ __device__ inline size_t qkv_heads_off(int b, int w, int h, int t, int d, int heads, int Tp) {
   const size_t base = (((size_t)b * 3 + w) * heads + h) * (size_t)Tp * 64;
-  return w != 2 ? base + (size_t)(t >> 7) * 8192 + (size_t)(d >> 3) * 1024 + (size_t)(t & 127) * 8 + (d & 7)
+  return w == 0 ? base + (size_t)(t >> 7) * 8192 + (size_t)(d >> 3) * 1024 + (size_t)(t & 127) * 8 + (d & 7)
                 : base + (size_t)(t >> 6) * 4096 + (size_t)(d >> 3) * 512 + (size_t)(t & 63) * 8 + (d & 7);
 }
 long long* s2d_get_trace();               // (the Whisper attention kernel writes its wait counters to the same buffer)

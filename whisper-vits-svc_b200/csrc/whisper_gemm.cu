@@ -154,7 +154,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
               const int bi = m / res_mod, t = m - bi * res_mod;
               const size_t o = qkv_heads_off(bi, w, hd, t, d, Dm >> 6, qkv_heads_tp(res_mod));
               *reinterpret_cast<uint4*>(ob + o) = *reinterpret_cast<const uint4*>(h);
-              *reinterpret_cast<uint4*>(ob + o + (w != 2 ? 1024 : 512)) = *reinterpret_cast<const uint4*>(h + 8);
+              *reinterpret_cast<uint4*>(ob + o + (w == 0 ? 1024 : 512)) = *reinterpret_cast<const uint4*>(h + 8);
             } else if (EPI == EPI_GELU_BF16_IMAGE) {  // A operand of the next GEMM
               __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
               *reinterpret_cast<uint4*>(ob + img_off(m, n0 + c0, N / GM_BK)) = *reinterpret_cast<const uint4*>(h);
