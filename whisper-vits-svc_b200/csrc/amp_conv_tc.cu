@@ -45,9 +45,8 @@ int p8_rows(int L) { return p8_rows_of(L); }
 constexpr int SP3_ROWS = 256;  // image rows per CTA (8 warps x 32)
 
 template <bool VEC>
-__device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, int L, const float (&fu)[12],
-                                        const float (&fdn)[12], const float* f_up, const float* f_dn, float a_,
-                                        float b_, float (&o)[8]) {
+__device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, int L, const SnakeTapsV& tp,
+                                        const float* f_up, const float* f_dn, float a_, float b_, float (&o)[8]) {
   // (the vector loads touch xr[n0-8 .. n0+16): keep them inside the row)
   if (VEC ? (n0 - 8 >= 0 && n0 + 16 <= L) : (n0 - 6 >= 0 && n0 + 13 <= L - 1)) {
     float x[24];  // xr[n0-8 .. n0+16)
@@ -58,29 +57,11 @@ __device__ __forceinline__ void sp3_run(const float* __restrict__ xr, int n0, in
         x[4 * q] = t4.x; x[4 * q + 1] = t4.y; x[4 * q + 2] = t4.z; x[4 * q + 3] = t4.w;
       }
     } else {
+      x[0] = x[1] = x[22] = x[23] = 0.f;   // never read
 #pragma unroll
       for (int q = 2; q < 22; ++q) x[q] = __ldg(xr + n0 - 8 + q);
     }
-    float vv[28];
-#pragma unroll
-    for (int p = 0; p < 14; ++p) {
-      float ue = x[p + 2] * fu[11];
-      ue = fmaf(x[p + 3], fu[9], ue); ue = fmaf(x[p + 4], fu[7], ue); ue = fmaf(x[p + 5], fu[5], ue);
-      ue = fmaf(x[p + 6], fu[3], ue); ue = fmaf(x[p + 7], fu[1], ue);
-      float uo = x[p + 3] * fu[10];
-      uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
-      uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
-      const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);   // fu carries UpSample1d's x2 gain
-      vv[2 * p] = fmaf(b_, se * se, ue);
-      vv[2 * p + 1] = fmaf(b_, so * so, uo);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float acc = 0.f;
-#pragma unroll
-      for (int k = 0; k < 12; ++k) acc = fmaf(vv[2 * i + 1 + k], fdn[k], acc);
-      o[i] = acc;
-    }
+    snake8_packed(x, tp, a_, 0.5f * b_, o);
   } else {  // a tap crosses a sequence end: replicate-clamped scalar path; rows outside [0, L) are zero
     const int mhi = 2 * L - 1;
     for (int i = 0; i < 8; ++i) {
@@ -106,7 +87,7 @@ template <bool VEC, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 snake_pack3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                    const float* __restrict__ ea, const float* __restrict__ inv_b,
-                   const float* __restrict__ fu_g, const float* __restrict__ fd_g, int C, int L, int Lp) {
+                   const float* __restrict__ fu_g, const float* __restrict__ fd_g, const SnakeTapsV tp, int C, int L, int Lp) {
   __shared__ float tile[8][32 * 9];   // per warp: [row][channel], row stride 9 -> conflict-free both ways
   __shared__ float f_up[12], f_dn[12];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -122,10 +103,7 @@ snake_pack3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, 
 #pragma unroll
   for (int i = 0; i < 8; ++i) o[i] = 0.f;
   if (ch < C && n0 < L && n0 + 8 > 0) {
-    float fu[12], fdn[12];
-#pragma unroll
-    for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }
-    sp3_run<VEC>(x + ((long long)b * C + ch) * L, n0, L, fu, fdn, f_up, f_dn, __ldg(ea + ch), __ldg(inv_b + ch), o);
+    sp3_run<VEC>(x + ((long long)b * C + ch) * L, n0, L, tp, f_up, f_dn, __ldg(ea + ch), __ldg(inv_b + ch), o);
   }
   float* tw = tile[warp];
 #pragma unroll
@@ -146,14 +124,25 @@ snake_pack3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, 
   if (lo) *reinterpret_cast<uint4*>(lo + img * 8) = *reinterpret_cast<const uint4*>(l2);
 }
 
+int snake_taps_from_device(const float* fu_dev, const float* fd_dev, SnakeTapsV* out) {
+  float h[24];
+  SVCB_CUDA_CHECK(cudaMemcpy(h, fu_dev, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  SVCB_CUDA_CHECK(cudaMemcpy(h + 12, fd_dev, 12 * sizeof(float), cudaMemcpyDeviceToHost));
+  *out = snake_taps_pack(h, h + 12);
+  return SVCB_OK;
+}
+
 size_t p8_image_bytes(int B, int C, int L) {  // one of hi / lo
   const int cp = (C + 15) / 16 * 16;
   return (size_t)B * (cp / 8) * p8_rows_of(L) * 16;
 }
 
 int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
-                      const float* fd, int B, int C, int L, cudaStream_t s) {
+                      const float* fd, int B, int C, int L, cudaStream_t s, const SnakeTapsV* taps) {
   if (B <= 0 || C <= 0 || L <= 0) return SVCB_OK;
+  SnakeTapsV tp;
+  if (taps) tp = *taps;
+  else SVCB_TRY(snake_taps_from_device(fu, fd, &tp));
   const int cp = (C + 15) / 16 * 16, Lp = p8_rows_of(L);
   char kname[64];
   snprintf(kname, sizeof(kname), "snake_pack_c%d", C);
@@ -165,8 +154,8 @@ int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const
     const bool vec = (L & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
     // 64 registers -> four CTAs (32 warps) per SM: each warp lives for one tile, so residency is
     // what hides its initial load latency (10.8 vs 11.4 ms/step with two CTAs)
-    if (vec) snake_pack3_kernel<true, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, C, L, Lp);
-    else snake_pack3_kernel<false, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, C, L, Lp);
+    if (vec) snake_pack3_kernel<true, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, tp, C, L, Lp);
+    else snake_pack3_kernel<false, 4><<<grid3, 256, 0, s>>>(x, h, l, ea, inv_b, fu, fd, tp, C, L, Lp);
     SVCB_LAUNCH_CHECK("snake_pack");
   }
   return SVCB_OK;

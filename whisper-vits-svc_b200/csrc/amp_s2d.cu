@@ -60,43 +60,6 @@ int s2d_rows(int L, int r) {                                         // Rp of an
 }
 size_t s2d_image_bytes(int B, int L, int r) { return (size_t)B * s2d::KC * s2d_rows(L, r) * 16; }
 
-// ------------------------------------------------------------------------------------------------ Snake
-// 8 outputs n0 .. n0+7 from the 24 inputs xw[0..24) = x[n0-8 .. n0+16)  (same arithmetic as
-// amp_conv_tc.cu:sp3_run; alias/resample.py:25-33, alias/act.py:79-92, alias/filter.py:86-94)
-// first / last: the run starts at sample 0 / ends at sample L-1 — the 2x signal is then replicate-padded
-// (alias/filter.py:90-91): values in front of v[0] (vv[0..6)) / behind v[2L-1] (vv[22..28)) repeat it.
-__device__ __forceinline__ void s2d_snake8(const float (&x)[24], const float (&fu)[12], const float (&fdn)[12],
-                                           float a_, float b_, float (&o)[8], bool first = false, bool last = false) {
-  float vv[28];
-#pragma unroll
-  for (int p = 0; p < 14; ++p) {
-    float ue = x[p + 2] * fu[11];
-    ue = fmaf(x[p + 3], fu[9], ue); ue = fmaf(x[p + 4], fu[7], ue); ue = fmaf(x[p + 5], fu[5], ue);
-    ue = fmaf(x[p + 6], fu[3], ue); ue = fmaf(x[p + 7], fu[1], ue);
-    float uo = x[p + 3] * fu[10];
-    uo = fmaf(x[p + 4], fu[8], uo); uo = fmaf(x[p + 5], fu[6], uo); uo = fmaf(x[p + 6], fu[4], uo);
-    uo = fmaf(x[p + 7], fu[2], uo); uo = fmaf(x[p + 8], fu[0], uo);
-    const float se = snake_sin(ue * a_), so = snake_sin(uo * a_);   // fu carries UpSample1d's x2 gain
-    vv[2 * p] = fmaf(b_, se * se, ue);
-    vv[2 * p + 1] = fmaf(b_, so * so, uo);
-  }
-  if (first) {
-#pragma unroll
-    for (int j = 0; j < 6; ++j) vv[j] = vv[6];
-  }
-  if (last) {
-#pragma unroll
-    for (int j = 22; j < 28; ++j) vv[j] = vv[21];
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    float acc = 0.f;
-#pragma unroll
-    for (int k = 0; k < 12; ++k) acc = fmaf(vv[2 * i + 1 + k], fdn[k], acc);
-    o[i] = acc;
-  }
-}
-
 __device__ __forceinline__ void s2d_store_octet(__nv_bfloat16* hi, __nv_bfloat16* lo, long long row_elem,
                                                 const float (&o)[8]) {
   __align__(16) __nv_bfloat162 h2[4], l2[4];
@@ -116,10 +79,7 @@ __device__ __forceinline__ void s2d_store_octet(__nv_bfloat16* hi, __nv_bfloat16
 __global__ void __launch_bounds__(256, 4)
 snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
                       const float* __restrict__ ea, const float* __restrict__ inv_b,
-                      const float* __restrict__ fu_g, const float* __restrict__ fd_g, int C, int L, int r, int Rp) {
-  __shared__ float f_up[12], f_dn[12];
-  if (threadIdx.x < 12) { f_up[threadIdx.x] = __ldg(fu_g + threadIdx.x); f_dn[threadIdx.x] = __ldg(fd_g + threadIdx.x); }
-  __syncthreads();
+                      const SnakeTapsV tp, int C, int L, int r, int Rp) {
   const int run = blockIdx.x * 256 + threadIdx.x;
   const int c = blockIdx.y, b = blockIdx.z;
   if (run * 8 >= L) return;
@@ -127,9 +87,7 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
   const float* xr = x + ((long long)b * C + c) * L;
   const int n0 = run * 8;
   const float a_ = __ldg(ea + c), b_ = __ldg(inv_b + c);
-  float out[8], xw[24], fu[12], fdn[12];
-#pragma unroll
-  for (int k = 0; k < 12; ++k) { fu[k] = 2.f * f_up[k]; fdn[k] = f_dn[k]; }
+  float out[8], xw[24];
   const bool first = n0 == 0, last = n0 + 8 == L;
   if (n0 - 8 >= 0 && n0 + 16 <= L) {
 #pragma unroll
@@ -141,7 +99,7 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
 #pragma unroll
     for (int j = 0; j < 24; ++j) xw[j] = __ldg(xr + min(max(n0 - 8 + j, 0), L - 1));
   }
-  s2d_snake8(xw, fu, fdn, a_, b_, out, first, last);
+  snake8_packed(xw, tp, a_, 0.5f * b_, out, first, last);   // common.cuh: packed f32x2 FIRs
   if (opr) {
     const int row = run / opr, o = c * opr + run % opr;
     const long long row_elem = ((((long long)b * s2d::KC + o) * Rp) + s2d::PADR + row) * 8;
@@ -164,18 +122,21 @@ snake_pack_s2d_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ h
 }
 
 int launch_snake_pack_s2d(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
-                          const float* fd, int B, int C, int L, cudaStream_t s) {
+                          const float* fd, int B, int C, int L, cudaStream_t s, const SnakeTapsV* taps) {
   const int r = C > 0 ? s2d::N / C : 0;
   if (B <= 0 || L <= 0 || C * r != s2d::N || (r != 4 && r != 8 && r != 16) || L % 8 || (reinterpret_cast<uintptr_t>(x) & 15)) {
     set_error("snake_pack_s2d: unsupported shape");
     return SVCB_E_BAD_SHAPE;
   }
+  SnakeTapsV tp;
+  if (taps) tp = *taps;
+  else SVCB_TRY(snake_taps_from_device(fu, fd, &tp));
   char kname[64];
   snprintf(kname, sizeof(kname), "snake_pack_s2d_c%d", C);
   KernelScope ks(kname, s, 0.0, 8.0 * B * C * (double)L, 70.0 * B * C * (double)L);
   dim3 grid((L / 8 + 255) / 256, C, B);
   snake_pack_s2d_kernel<<<grid, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ea,
-                                             inv_b, fu, fd, C, L, r, s2d_rows(L, r));
+                                             inv_b, tp, C, L, r, s2d_rows(L, r));
   SVCB_LAUNCH_CHECK("snake_pack_s2d");
   return SVCB_OK;
 }

@@ -66,6 +66,7 @@ static void tc_tiling(ConvW& w) {
 struct SnakeW {
   const float *ea = nullptr, *ib = nullptr, *fu = nullptr, *fd = nullptr;
   float fu_h[12] = {0}, fd_h[12] = {0};   // host copies of the 12 + 12 alias-filter taps (read back once at model creation)
+  SnakeTapsV tapsv() const { return snake_taps_pack(fu_h, fd_h); }
 };
 static void snake_taps_to(const SnakeW& w, AmpS2dParams& q) {
   for (int k = 0; k < 12; ++k) { q.fu2[k] = 2.f * w.fu_h[k]; q.fdn[k] = w.fd_h[k]; }
@@ -386,7 +387,8 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
       // narrow stages: every link = block-Toeplitz tcgen05 conv with the next SnakeAlias in its epilogue
       const int Rp = s2d_rows(L, R.s2d_r);
       void *ia_hi = S2D[0], *ia_lo = S2D[1], *ib_hi = S2D[2], *ib_lo = S2D[3];
-      RUN(launch_snake_pack_s2d(X, ia_hi, ia_lo, R.act[0].ea, R.act[0].ib, R.act[0].fu, R.act[0].fd, B, ch, L, s));
+      const SnakeTapsV tv0 = R.act[0].tapsv();
+      RUN(launch_snake_pack_s2d(X, ia_hi, ia_lo, R.act[0].ea, R.act[0].ib, R.act[0].fu, R.act[0].fd, B, ch, L, s, &tv0));
       const float* cur = X;
       for (int d = 0; d < 3; ++d) {
         AmpS2dParams q;
@@ -440,10 +442,11 @@ static int run_amp_stage(const svcb_model* m, Ctx& ctx, int stage, const float* 
         q.B = B; q.C = ch; q.Cp = (ch + 15) / 16 * 16; q.L = L; q.K = R.k; q.nsplit = prec == 1 ? 1 : 3;
         q.Lp = p8_rows(L); q.a_hi = IMG_HI; q.a_lo = q.nsplit == 3 ? IMG_LO : nullptr;
         void* lo = q.nsplit == 3 ? IMG_LO : nullptr;
-        RUN(launch_snake_pack(cur, IMG_HI, lo, a1.ea, a1.ib, a1.fu, a1.fd, B, ch, L, s));
+        const SnakeTapsV tv1 = a1.tapsv(), tv2 = a2.tapsv();
+        RUN(launch_snake_pack(cur, IMG_HI, lo, a1.ea, a1.ib, a1.fu, a1.fd, B, ch, L, s, &tv1));
         q.y = T2; q.wpk = R.c1_tc[d]; q.bias = R.c1[d].b; q.dil = R.dil[d];
         RUN(launch_amp_conv_tc(q, s));
-        RUN(launch_snake_pack(T2, IMG_HI, lo, a2.ea, a2.ib, a2.fu, a2.fd, B, ch, L, s));
+        RUN(launch_snake_pack(T2, IMG_HI, lo, a2.ea, a2.ib, a2.fu, a2.fd, B, ch, L, s, &tv2));
         q.wpk = R.c2_tc[d]; q.bias = R.c2[d].b; q.dil = 1; q.res = cur;
         if (d < 2) {
           q.y = (d == 0) ? RA : RB;

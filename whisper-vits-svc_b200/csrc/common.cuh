@@ -92,6 +92,66 @@ __device__ __forceinline__ float snake_cos2(float x) {
   return __cosf(r + r);
 }
 
+// The 12 + 12 alias-filter taps of a SnakeAlias BY VALUE, paired for packed f32x2 FMAs (FFMA2 takes a uniform-
+// register pair as an operand: no register holds a tap).  fup[j] = 2 * (up[11-2j], up[10-2j]) (UpSample1d's
+// ratio gain folded in, exact); fdp[m] = (dn[2m+1], dn[2m+2]); the decimator's two end taps apart.
+struct SnakeTapsV {
+  float2 fup[6], fdp[5];
+  float fd0, fd11;
+};
+inline SnakeTapsV snake_taps_pack(const float* up12, const float* dn12) {
+  SnakeTapsV t;
+  for (int j = 0; j < 6; ++j) t.fup[j] = make_float2(2.f * up12[11 - 2 * j], 2.f * up12[10 - 2 * j]);
+  for (int m = 0; m < 5; ++m) t.fdp[m] = make_float2(dn12[2 * m + 1], dn12[2 * m + 2]);
+  t.fd0 = dn12[0]; t.fd11 = dn12[11];
+  return t;
+}
+// device taps -> SnakeTapsV through a synchronous copy (unit-test entry points; the model keeps host copies)
+int snake_taps_from_device(const float* fu_dev, const float* fd_dev, SnakeTapsV* out);
+
+#ifdef __CUDACC__
+// SnakeAlias of 8 consecutive samples n0 .. n0+7 from the 24 inputs x[0..24) = signal[n0-8 .. n0+16)
+// (alias/resample.py:25-33 up x2, alias/act.py:79-92 Snake, alias/filter.py:86-94 + resample.py:52-58 down x2),
+// all FIR and range-reduction arithmetic as packed f32x2 FMAs: the pair V[p] = (v[2p], v[2p+1]) of the 2x signal
+// is one FFMA2 chain over the input pairs (x[p+2+j], x[p+3+j]); sin^2 = (1 - cos 2r) / 2 with the two-constant
+// reduction of snake_cos2; the decimator sums five pair products + its two end taps.  hb = 0.5 / (exp(beta) + eps).
+// first / last: the run starts at sample 0 / ends at the last sample — the 2x signal is replicate-padded there.
+__device__ __forceinline__ void snake8_packed(const float (&x)[24], const SnakeTapsV& tp, float a_, float hb_, float (&o)[8],
+                                              bool first = false, bool last = false) {
+  float2 V[14];
+  const float2 a2 = make_float2(a_, a_), hb2 = make_float2(hb_, hb_), nhb2 = make_float2(-hb_, -hb_);
+#pragma unroll
+  for (int p = 0; p < 14; ++p) {
+    float2 U = __fmul2_rn(make_float2(x[p + 2], x[p + 3]), tp.fup[0]);
+#pragma unroll
+    for (int j = 1; j < 6; ++j) U = __ffma2_rn(make_float2(x[p + 2 + j], x[p + 3 + j]), tp.fup[j], U);
+    const float2 t = __fmul2_rn(U, a2);
+    const float2 kq = __fadd2_rn(__ffma2_rn(t, make_float2(0.3183098861837907f, 0.3183098861837907f), make_float2(12582912.f, 12582912.f)),
+                                 make_float2(-12582912.f, -12582912.f));
+    float2 rr = __ffma2_rn(kq, make_float2(-3.140625f, -3.140625f), t);
+    rr = __ffma2_rn(kq, make_float2(-9.676535897932e-4f, -9.676535897932e-4f), rr);
+    rr = __fadd2_rn(rr, rr);
+    const float2 cs = make_float2(__cosf(rr.x), __cosf(rr.y));
+    V[p] = __ffma2_rn(nhb2, cs, __fadd2_rn(U, hb2));
+  }
+  if (first) {   // v[0 .. 6) = v[6]
+    const float2 e = make_float2(V[3].x, V[3].x);
+    V[0] = e; V[1] = e; V[2] = e;
+  }
+  if (last) {    // v[22 .. 28) = v[21]
+    const float2 e = make_float2(V[10].y, V[10].y);
+    V[11] = e; V[12] = e; V[13] = e;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {   // o_i = sum_k v[2i + 1 + k] dn[k]
+    float2 acc = __fmul2_rn(V[i + 1], tp.fdp[0]);
+#pragma unroll
+    for (int m = 1; m < 5; ++m) acc = __ffma2_rn(V[i + 1 + m], tp.fdp[m], acc);
+    o[i] = fmaf(V[i].y, tp.fd0, fmaf(V[i + 6].x, tp.fd11, acc.x + acc.y));
+  }
+}
+#endif
+
 // ----------------------------------------------------------------------------- conv1d
 enum ConvFlags : int {
   CONV_IN_MASK = 1,    // x[b,:,t] treated as 0 for t >= lengths[b]
@@ -140,8 +200,9 @@ struct AmpConvParams {
 int launch_amp_conv_tc(const AmpConvParams& p, cudaStream_t s);
 size_t amp_conv_tc_smem_bytes(int Cp, int K, int dil, int nsplit);
 // SnakeAlias(x[B,C,L]) -> bf16 hi (and lo, may be null) operand images
+// taps: host copy of the filter taps, or null (then read back from fu / fd with a synchronous copy: test entry points)
 int launch_snake_pack(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
-                      const float* fd, int B, int C, int L, cudaStream_t s);
+                      const float* fd, int B, int C, int L, cudaStream_t s, const SnakeTapsV* taps = nullptr);
 size_t p8_image_bytes(int B, int C, int L);
 int p8_rows(int L);
 
@@ -183,7 +244,7 @@ long long* s2d_get_trace();               // (the Whisper attention kernel write
 void s2d_set_trace(long long* dev_buf);   // test hook: trace buffer used by the next launches (null = off)
 int launch_amp_s2d_link(const AmpS2dParams& p, cudaStream_t s);
 int launch_snake_pack_s2d(const float* x, void* hi, void* lo, const float* ea, const float* inv_b, const float* fu,
-                          const float* fd, int B, int C, int L, cudaStream_t s);
+                          const float* fd, int B, int C, int L, cudaStream_t s, const SnakeTapsV* taps = nullptr);
 int launch_s2d_unpack(const void* hi, const void* lo, float* y, int B, int C, int L, cudaStream_t s);
 int s2d_rows(int L, int r);
 size_t s2d_image_bytes(int B, int L, int r);
