@@ -128,6 +128,7 @@ struct svcb_model {
   std::vector<svcb::UpStage> ups;
   std::vector<svcb::ResBlock> res;
   svcb::SnakeW post_act;
+  std::vector<float> conv_post_h;   // host copy of conv_post's taps [cin][7] (kernel parameters of the fused tail)
 };
 
 namespace svcb {
@@ -628,6 +629,10 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     x = ACC; ch = chn; L = Ln;
   }
   // activation_post + conv_post + tanh (generator.py:196-199)
+  if (!m->conv_post.b && post_fused_supported(ch, L, m->conv_post.k, x, wave)) {
+    RUN(launch_post_fused(x, wave, m->post_act.ea, m->post_act.ib, m->post_act.tapsv(), m->conv_post_h.data(), B, ch, L, s));
+    return SVCB_OK;
+  }
   RUN(launch_snake_alias(x, T1, m->post_act.ea, m->post_act.ib, m->post_act.fu, m->post_act.fd, B, ch, L, s));
   {
     ConvParams p = std_conv(m->conv_post, T1, wave, B, L, L, 3);
@@ -782,6 +787,16 @@ static int resolve(svcb_model* m) {
   if (!R.ok) {
     set_error("tensor missing or too small in packed blob: " + R.missing);
     return SVCB_E_MISSING_TENSOR;
+  }
+  {  // packed [cin][k][cout_pad]: keep output channel 0 of every tap on the host
+    const ConvW& w = m->conv_post;
+    std::vector<float> packed((size_t)w.cin * w.k * w.cout_pad);
+    if (cudaMemcpy(packed.data(), w.w, packed.size() * sizeof(float), cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("reading conv_post back failed");
+      return SVCB_E_CUDA;
+    }
+    m->conv_post_h.resize((size_t)w.cin * w.k);
+    for (int i = 0; i < w.cin * w.k; ++i) m->conv_post_h[i] = packed[(size_t)i * w.cout_pad];
   }
   return SVCB_OK;
 }

@@ -106,6 +106,9 @@ inline SnakeTapsV snake_taps_pack(const float* up12, const float* dn12) {
   t.fd0 = dn12[0]; t.fd11 = dn12[11];
   return t;
 }
+bool post_fused_supported(int C, int L, int K, const float* x, const float* wave);
+int launch_post_fused(const float* x, float* wave, const float* ea, const float* inv_b, const SnakeTapsV& tp,
+                      const float* w_host, int B, int C, int L, cudaStream_t s);
 // device taps -> SnakeTapsV through a synchronous copy (unit-test entry points; the model keeps host copies)
 int snake_taps_from_device(const float* fu_dev, const float* fd_dev, SnakeTapsV* out);
 

@@ -77,4 +77,87 @@ int launch_snake_alias(const float* x, float* y, const float* ea, const float* i
   return SVCB_OK;
 }
 
+// ------------------------------------------------------------------------------------ generator tail
+// activation_post + conv_post + tanh (vits_decoder/generator.py:196-199) in one pass: wave[b, t] =
+// tanh(sum_c sum_k w[c][k] * SnakeAlias_c(x[b, c, :])[t + k - PAD]) with the conv's zero padding.  The two
+// separate kernels moved the 10-channel full-rate signal through HBM three times and the 10 -> 1 conv ran at
+// 1/24 of its bandwidth roof (1.44 ms); here a thread computes one run of 8 Snake values per channel
+// (snake8_packed), the three values its conv taps need from either neighbouring run come through a
+// double-buffered shared row, and only the waveform is written.
+constexpr int PF_RUNS = 256, PF_OUT_RUNS = PF_RUNS - 2, PF_MAXC = 16, PF_K = 7;
+
+struct PostTaps { float w[PF_MAXC][PF_K]; };
+
+__global__ void __launch_bounds__(PF_RUNS)
+post_fused_kernel(const float* __restrict__ x, float* __restrict__ wave, const float* __restrict__ ea,
+                  const float* __restrict__ inv_b, const SnakeTapsV tp, const PostTaps pw, int C, int L) {
+  __shared__ __align__(16) float srow[2][PF_RUNS * 8];
+  const int tid = threadIdx.x, b = blockIdx.y;
+  const int n0 = blockIdx.x * (PF_OUT_RUNS * 8) - 8 + tid * 8;   // this thread's run of Snake values
+  const bool inside = n0 >= 0 && n0 < L;                          // outside the sequence: the conv's zero padding
+  const bool produces = tid >= 1 && tid <= PF_OUT_RUNS && inside;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int c = 0; c < C; ++c) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (inside) {
+      const float* xr = x + ((long long)b * C + c) * L;
+      float xw[24];
+      if (n0 - 8 >= 0 && n0 + 16 <= L) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(xr + n0 - 8) + q);
+          xw[4 * q] = t4.x; xw[4 * q + 1] = t4.y; xw[4 * q + 2] = t4.z; xw[4 * q + 3] = t4.w;
+        }
+      } else {   // replicate padding of x (alias/resample.py:28) = clamped loads
+#pragma unroll
+        for (int j = 0; j < 24; ++j) xw[j] = __ldg(xr + min(max(n0 - 8 + j, 0), L - 1));
+      }
+      snake8_packed(xw, tp, __ldg(ea + c), 0.5f * __ldg(inv_b + c), v, n0 == 0, n0 + 8 == L);
+    }
+    float* sr = srow[c & 1];
+    *reinterpret_cast<float4*>(sr + tid * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(sr + tid * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    __syncthreads();
+    if (produces) {
+      const float4 lf = *reinterpret_cast<const float4*>(sr + tid * 8 - 4);   // values 4..7 of the run before
+      const float4 rt = *reinterpret_cast<const float4*>(sr + tid * 8 + 8);   // values 0..3 of the run behind
+      const float e[14] = {lf.y, lf.z, lf.w, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], rt.x, rt.y, rt.z};
+#pragma unroll
+      for (int k = 0; k < PF_K; ++k) {
+        const float wk = pw.w[c][k];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(e[i + k], wk, acc[i]);
+      }
+    }
+  }
+  if (produces) {
+    float* o = wave + (long long)b * L + n0;
+    *reinterpret_cast<float4*>(o) = make_float4(tanhf(acc[0]), tanhf(acc[1]), tanhf(acc[2]), tanhf(acc[3]));
+    *reinterpret_cast<float4*>(o + 4) = make_float4(tanhf(acc[4]), tanhf(acc[5]), tanhf(acc[6]), tanhf(acc[7]));
+  }
+}
+
+bool post_fused_supported(int C, int L, int K, const float* x, const float* wave) {
+  return C >= 1 && C <= PF_MAXC && K == PF_K && L % 8 == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(wave)) & 15) == 0;
+}
+
+// w_host: the conv_post taps [C][7] on the host (out channel 0)
+int launch_post_fused(const float* x, float* wave, const float* ea, const float* inv_b, const SnakeTapsV& tp,
+                      const float* w_host, int B, int C, int L, cudaStream_t s) {
+  if (B <= 0 || L <= 0) return SVCB_OK;
+  if (!post_fused_supported(C, L, PF_K, x, wave)) { set_error("post_fused: unsupported shape"); return SVCB_E_BAD_SHAPE; }
+  PostTaps pw;
+  for (int c = 0; c < PF_MAXC; ++c)
+    for (int k = 0; k < PF_K; ++k) pw.w[c][k] = c < C ? w_host[c * PF_K + k] : 0.f;
+  dim3 grid((L / 8 + PF_OUT_RUNS - 1) / PF_OUT_RUNS, B);
+  KernelScope ks("post_fused", s, 2.0 * PF_K * B * C * (double)L, 4.0 * B * (C + 1) * (double)L, 70.0 * B * C * (double)L);
+  post_fused_kernel<<<grid, PF_RUNS, 0, s>>>(x, wave, ea, inv_b, tp, pw, C, L);
+  SVCB_LAUNCH_CHECK("post_fused");
+  return SVCB_OK;
+}
+
 }  // namespace svcb
