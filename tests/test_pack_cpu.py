@@ -51,6 +51,50 @@ def test_polyphase_transposed_conv(k, s):
     assert torch.allclose(y, ref, atol=1e-5), (y - ref).abs().max()
 
 
+@pytest.mark.parametrize("k,s", [(8, 4), (4, 2), (16, 8)])
+def test_ups_combined_is_the_transposed_conv(k, s):
+    """pack.ups_combined: the polyphase sub-filters as ONE Conv1d with rate * Cout channels and M + 1 taps whose
+    channel co * rate + slot at frame i is sample rate * i + slot of ConvTranspose1d (generator.py:183) —
+    what csrc/conv_tc.cu's interleaved epilogue (ConvTcParams::ilv) stores."""
+    torch.manual_seed(k + s)
+    cin, cout, T = 6, 4, 19
+    w = torch.randn(cin, cout, k)
+    b = torch.randn(cout)
+    x = torch.randn(2, cin, T)
+    p = (k - s) // 2
+    ref = F.conv_transpose1d(x, w, b, stride=s, padding=p)
+    assert ref.shape[-1] == T * s
+    M = (k + s - 1) // s
+    subs = []
+    for r in range(s):
+        sub = torch.zeros(cout, cin, M)
+        for jp in range(M):
+            j = r + s * (M - 1 - jp)
+            if j < k:
+                sub[:, :, jp] = w[:, :, j].t()
+        subs.append(sub)
+    wc, bc = pack.ups_combined(subs, b, s, p)
+    assert wc.shape == (cout * s, cin, M + 1)
+    yc = F.conv1d(F.pad(x, (M - 1, 1)), wc, bc)              # frame i reads x[i - (M-1) .. i + 1]
+    got = yc.view(2, cout, s, T).permute(0, 1, 3, 2).reshape(2, cout, T * s)
+    assert torch.allclose(got, ref, atol=1e-5), (got - ref).abs().max()
+    # with the noise conv of the stage riding as extra input channels gathered from the padded source
+    sf, kch, PADF = 4, 8, 32
+    src = torch.randn(2, 1, T * s * sf)
+    wn, bn = torch.randn(cout, 1, 2 * sf), torch.randn(cout)
+    ref2 = ref + F.conv1d(src, wn, bn, stride=sf, padding=sf // 2)
+    wc2, bc2 = pack.ups_combined(subs, b, s, p, wn, bn, sf, kch)
+    cin1 = (cin + kch - 1) // kch * kch
+    nc = s * sf + sf
+    assert wc2.shape == (cout * s, cin1 + nc, M + 1)
+    srcp = F.pad(src[:, 0], (PADF, 128))
+    x2 = torch.stack([srcp[:, PADF - sf // 2 + ci: PADF - sf // 2 + ci + sf * s * T: sf * s] for ci in range(nc)], 1)
+    xin = torch.cat([x, torch.zeros(2, cin1 - cin, T), x2], 1)
+    yc2 = F.conv1d(F.pad(xin, (M - 1, 1)), wc2, bc2)
+    got2 = yc2.view(2, cout, s, T).permute(0, 1, 3, 2).reshape(2, cout, T * s)
+    assert torch.allclose(got2, ref2, atol=1e-4), (got2 - ref2).abs().max()
+
+
 def test_packed_model_tensor_inventory(hp, sd):
     cfg = pack.config_from_hp(hp)
     items = dict(pack.pack_svc_state_dict(sd, cfg))

@@ -89,6 +89,8 @@ struct UpStage {
   const float* bias;
   ConvW noise;
   ConvW noise_tc;            // long noise filter as a 2-tap conv over the space-to-depth source
+  int comb_cin1 = 0, comb_cin2 = 0;   // comb's input channels: [0, comb_cin1) the stage input (zero padded), then windows of the source
+  ConvW comb;                // all phases as ONE conv with rate * Cout channels, taps + 1 taps (pack.py:ups_combined) or tc == null
   int rate, k, pad, taps;
 };
 struct ResBlock {
@@ -548,6 +550,22 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
     fp.sf = last ? 1 : sf; fp.padn = last ? 0 : sf / 2; fp.cout_pad = us.noise.cout_pad; fp.Ltot = Ltot;
     size_t slab = 0;
     const bool fused_up = c.precision != 0 && fuse_noise && ups_fused_supported(ch, chn, us.rate, us.taps, Kn);
+    // wide stages: every phase AND the stage's noise conv in one tensor-core conv whose epilogue stores the
+    // interleaved samples — the stage input is read once, X is written once
+    const bool comb_up = c.precision != 0 && !fused_up && us.comb.tc != nullptr && !last && Kn == 2 * sf && sf / 2 <= SRC_PADF;
+    if (comb_up) {
+      fp.src = nullptr;
+      const ConvW& w = us.comb;
+      ConvTcParams q;
+      q.x = x; q.sxb = (long long)ch * L; q.sxc = L; q.sxt = 1;
+      q.wpk = w.tc; q.bias = w.b; q.y = X;
+      q.B = B; q.Cin = ch; q.cin_pad = w.cin_pad; q.Cout = w.cout; q.Tin = L; q.Tout = L;
+      q.K = w.k; q.dil = 1; q.pad = us.taps - 1; q.kch = w.kch; q.bn = w.bn; q.ntiles = w.ntiles;
+      q.nsplit = c.precision == 1 ? 1 : 3; q.ilv = us.rate;
+      q.x2 = SRCP + (SRC_PADF - sf / 2); q.sx2b = Lpad; q.sx2t = (long long)sf * us.rate;
+      q.cin1 = us.comb_cin1; q.cin2 = us.comb_cin2;
+      RUN(launch_conv_tc(q, s));
+    }
     if (fused_up) {  // narrow stages: transposed conv + noise conv + biases in one fp32 pass
       UpsFusedParams q;
       q.x = x; q.wph[0] = us.phase[0].w; q.wph[1] = us.phase[1].w; q.bias = us.bias;
@@ -557,7 +575,7 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
       q.cout_pad_n = us.noise.cout_pad; q.Ltot = Ltot;
       RUN(launch_ups_fused(q, s));
     }
-    for (int r = 0; r < us.rate && !fused_up; ++r) {
+    for (int r = 0; r < us.rate && !fused_up && !comb_up; ++r) {
       ConvParams p = std_conv(us.phase[r], x, nullptr, B, L, Ln, us.taps - 1);
       p.bias = nullptr;
       const int pr = us.pad - r;
@@ -583,8 +601,10 @@ static int run_generator(const svcb_model* m, Ctx& ctx, const float* spk, const 
         RUN(launch_conv1d(p, s));
       }
     }
-    if (!ctx.dry && !fused_up) SVCB_TRY(launch_ups_finalize(fp, B, s));
-    if (!fuse_noise && c.precision != 0 && us.noise_tc.tc && sf <= 2 * SRC_PADF && !last) {
+    if (!ctx.dry && !fused_up && !comb_up) SVCB_TRY(launch_ups_finalize(fp, B, s));
+    if (comb_up) {
+      // (noise conv already inside the combined convolution)
+    } else if (!fuse_noise && c.precision != 0 && us.noise_tc.tc && sf <= 2 * SRC_PADF && !last) {
       // long noise filter as Conv1d(sf -> C, K=2) over the space-to-depth view of the padded source:
       // x[b, ci, t] = srcp[b][32 - sf/2 + sf*t + ci]
       const ConvW& w = us.noise_tc;
@@ -736,6 +756,17 @@ static int resolve(svcb_model* m) {
     for (int r = 0; r < us.rate; ++r)
       us.phase.push_back(R.conv(p + ".ph" + std::to_string(r), ch, ch / 2, us.taps, false, true));
     us.bias = R.get(p + ".b", ch / 2);
+    if (us.rate == 4 && us.taps == 2 && i + 1 < c.n_ups) {   // pack.py:UPS_COMBINED_RATES (+ the stage's noise conv)
+      int sfc = 1;
+      for (int k2 = i + 1; k2 < c.n_ups; ++k2) sfc *= c.up_rates[k2];
+      ConvW& w = us.comb;
+      us.comb_cin1 = (ch + 31) / 32 * 32;
+      us.comb_cin2 = us.rate * sfc + sfc;             // source samples a frame's rate outputs reach (filter 2 sf, stride sf)
+      w.cin = us.comb_cin1 + us.comb_cin2; w.cout = us.rate * (ch / 2); w.k = us.taps + 1; w.cout_pad = (w.cout + 7) / 8 * 8;
+      tc_tiling(w);
+      w.tc = reinterpret_cast<const uint8_t*>(R.get(p + ".comb.tc", (uint64_t)w.k * 2 * w.cin_pad * w.ntiles * w.bn / 2));
+      w.b = R.get(p + ".comb.b", w.cout);
+    }
     ch /= 2;
   }
   ch = c.gen_initial_channel;

@@ -299,6 +299,13 @@ struct ConvTcParams {
   int kch = 64, bn = 128, ntiles = 1;
   int nsplit = 3;
   int flags = 0, act = 0;
+  // optional second input (pack.py:ups_combined): packed input channels cin1 .. cin1 + cin2 are x2[b][t * sx2t + c]
+  // (channel-contiguous, e.g. windows of the padded harmonic source); channels Cin .. cin1 are zero padding
+  const float* x2 = nullptr;
+  long long sx2b = 0, sx2t = 0;
+  int cin1 = 0, cin2 = 0;
+  int ilv = 0;   // 2 or 4: output channel cp = co * ilv + s is sample ilv * t + s of y[b, co, :] (y is [B, Cout / ilv, Tout * ilv]):
+                 // the combined polyphase form of a transposed convolution (pack.py:ups_combined); no res / accumulate / gate
 };
 int launch_conv_tc(const ConvTcParams& p, cudaStream_t s);
 

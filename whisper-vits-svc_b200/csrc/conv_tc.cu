@@ -79,6 +79,7 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
   if (warp < 4) {
     // ---------------------------------------------------------------- A producers
     const float* xb = p.x + (long long)b * p.sxb;
+    const float* x2b = p.x2 ? p.x2 + (long long)b * p.sx2b : nullptr;
     for (int cc = 0; cc < ncc; ++cc) {
       const int buf = cc & 1;
       if (cc >= 2) tc::mbar_wait(&a_empty[buf], (uint32_t)(((cc >> 1) - 1) & 1));
@@ -90,7 +91,11 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
         const int c0 = cc * p.kch + kc * 8;
         float v[8];
         const bool row_ok = tau >= 0 && tau < p.Tin && (!(p.flags & CONV_IN_MASK) || tau < len);
-        if (row_ok) {
+        if (row_ok && x2b && c0 >= p.cin1) {   // second input: channel-contiguous windows (unaligned)
+          const float* s2 = x2b + (long long)tau * p.sx2t + (c0 - p.cin1);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = (c0 - p.cin1 + e < p.cin2) ? __ldg(s2 + e) : 0.f;
+        } else if (row_ok) {
           if (p.sxc == 1 && c0 + 8 <= p.Cin) {  // channel-contiguous input: two 16-byte loads
             const float4* s4 = reinterpret_cast<const float4*>(xb + (long long)tau * p.sxt + c0);
             const float4 u0 = __ldg(s4), u1 = __ldg(s4 + 1);
@@ -131,6 +136,31 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
     const bool keep = !(p.flags & CONV_OUT_MASK) || t < len;
     float* yb = p.y + (long long)b * cout_real * p.Tout;
     const float* rb = p.res ? p.res + (long long)b * cout_real * p.Tout : nullptr;
+    if (p.ilv) {   // interleaved store: ilv consecutive samples of one channel per thread (one 8 / 16-byte store)
+      float* yi = p.y + (long long)b * p.Cout * p.Tout;   // = [Cout / ilv][Tout * ilv]
+      for (int c0 = grp * 16; c0 < p.bn; c0 += 32) {
+        uint32_t v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
+        tc::tmem_ld_wait();
+        if (t < p.Tout) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const int cp = nt * p.bn + c0 + j;
+            if (cp < p.Cout) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = ct_act(__uint_as_float(v[j + e]) + (p.bias ? __ldg(p.bias + cp + e) : 0.f), p.act);
+              if (p.ilv == 4) {
+                *reinterpret_cast<float4*>(yi + ((long long)(cp >> 2) * p.Tout + t) * 4) = make_float4(o[0], o[1], o[2], o[3]);
+              } else {
+                *reinterpret_cast<float2*>(yi + ((long long)(cp >> 1) * p.Tout + t) * 2) = make_float2(o[0], o[1]);
+                *reinterpret_cast<float2*>(yi + ((long long)((cp >> 1) + 1) * p.Tout + t) * 2) = make_float2(o[2], o[3]);
+              }
+            }
+          }
+        }
+      }
+    } else
     for (int c0 = grp * 16; c0 < p.bn; c0 += 32) {
       uint32_t v[16];
       tc::tmem_ld16(tmem + ((uint32_t)(wq * 32) << 16) + (uint32_t)c0, v);
@@ -249,6 +279,15 @@ int launch_conv_tc(const ConvTcParams& p, cudaStream_t s) {
   if ((p.kch != 32 && p.kch != 64) || p.cin_pad % p.kch || p.bn % 16 || p.bn < 16 || p.bn > 256 ||
       p.ntiles * p.bn < p.Cout || (p.nsplit != 1 && p.nsplit != 3) || p.Tout > p.Tin) {
     set_error("conv_tc: unsupported tiling (stride-1 'same' convolutions only)");
+    return SVCB_E_BAD_SHAPE;
+  }
+  if (p.x2 && (p.cin1 % 8 || p.cin1 < p.Cin || p.cin1 + p.cin2 > p.cin_pad)) {
+    set_error("conv_tc: second input must start at a multiple of 8 channels behind the first");
+    return SVCB_E_BAD_SHAPE;
+  }
+  if (p.ilv && ((p.ilv != 2 && p.ilv != 4) || p.Cout % 4 || p.res || (p.flags & (CONV_ACCUM | CONV_GATE | CONV_OUT_MASK)) ||
+                (reinterpret_cast<uintptr_t>(p.y) & 15))) {
+    set_error("conv_tc: interleaved output needs ilv in {2, 4}, Cout % 4 == 0, a 16-byte aligned y and a plain epilogue");
     return SVCB_E_BAD_SHAPE;
   }
   // a 2-deep weight ring when that lets two CTAs share an SM (one CTA's epilogue then overlaps the

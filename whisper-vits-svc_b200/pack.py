@@ -146,6 +146,44 @@ def pack_conv_tc_general(w: torch.Tensor) -> torch.Tensor:
     return img.view(torch.float32).reshape(-1)
 
 
+UPS_COMBINED_RATES = (4,)   # stages whose polyphase sub-filters are also packed as ONE convolution (below)
+
+
+def ups_combined(subs, bias: torch.Tensor, rate: int, pad: int, wn: torch.Tensor = None, bn: torch.Tensor = None,
+                 sf: int = 0, kch: int = 32):
+    """The `rate` polyphase sub-filters of a ConvTranspose1d (M taps each, [Cout, Cin, M]) as ONE Conv1d with
+    rate * Cout output channels and M + 1 taps (padding M - 1): output channel co * rate + s at frame i is the
+    transposed conv's output sample rate * i + s of channel co.  Phase r starts at frame q0_r = ceil((pad - r) /
+    rate) (0 when r >= pad) and lands on slot s_r = rate * q0_r + r - pad; a phase with q0 = 1 reads x one frame
+    later, i.e. its taps sit one position further right in the common window.  The tensor-core conv then reads
+    the stage input once instead of `rate` times and its epilogue stores `rate` consecutive samples per thread
+    (csrc/conv_tc.cu, ConvTcParams::ilv) — no phase scratch, no interleave pass.
+
+    With wn ([Cout, 1, 2 sf], bn): noise_convs[i] (Conv1d(1, Cout, 2 sf, stride sf, padding sf / 2) over the
+    harmonic source, generator.py:185-186) rides in the same GEMM as extra input channels behind the main ones
+    (padded to a multiple of kch): at frame i channel ci' is source sample sf * rate * i - sf / 2 + ci', ci' <
+    rate * sf + sf, and output slot s takes tap j of the noise filter from channel s * sf + j at the window tap
+    that reads frame i.  (ConvTcParams::x2: the kernel gathers those channels from the padded source.)"""
+    cout, cin, M = subs[0].shape
+    cin1 = (cin + kch - 1) // kch * kch if wn is not None else cin
+    nc = rate * sf + wn.shape[-1] - sf if wn is not None else 0
+    w = torch.zeros(cout * rate, cin1 + nc, M + 1)
+    b = torch.zeros(cout * rate)
+    for r in range(rate):
+        q0 = (pad - r + rate - 1) // rate if pad > r else 0
+        assert q0 in (0, 1)
+        s = rate * q0 + r - pad
+        assert 0 <= s < rate
+        w[s::rate, :cin, q0:q0 + M] = subs[r]
+        b[s::rate] = bias
+    if wn is not None:
+        assert wn.shape[-1] == 2 * sf and wn.shape[1] == 1
+        for s in range(rate):
+            w[s::rate, cin1 + s * sf:cin1 + s * sf + 2 * sf, M - 1] = wn[:, 0, :]
+            b[s::rate] += bn
+    return w, b
+
+
 def config_from_hp(hp, precision: int = 0) -> dict:
     rates = [int(x) for x in hp.gen.upsample_rates]
     ks = [int(x) for x in hp.gen.upsample_kernel_sizes]
@@ -223,16 +261,25 @@ def pack_svc_state_dict(sd: Dict[str, torch.Tensor], cfg: dict) -> List[Tuple[st
     for i, (rate, k) in enumerate(zip(cfg["up_rates"], cfg["up_kernels"])):
         w = fold_weight_norm(sd, f"dec.ups.{i}")  # [Cin, Cout, k]
         M = (k + rate - 1) // rate
+        subs = []
         for r in range(rate):
             sub = torch.zeros(w.shape[1], w.shape[0], M)
             for jp in range(M):
                 j = r + rate * (M - 1 - jp)
                 if j < k:
                     sub[:, :, jp] = w[:, :, j].t()
+            subs.append(sub)
             put(f"dec.ups.{i}.ph{r}.w", pack_conv(sub))
             put(f"dec.ups.{i}.ph{r}.tc", pack_conv_tc_general(sub))
         put(f"dec.ups.{i}.b", sd[f"dec.ups.{i}.bias"])
         wn = sd[f"dec.noise_convs.{i}.weight"]
+        if rate in UPS_COMBINED_RATES and M == 2:
+            sf_c = int(np.prod(cfg["up_rates"][i + 1:])) if i + 1 < len(cfg["up_rates"]) else 1
+            assert wn.shape[-1] == 2 * sf_c, "combined up-sampling stage: noise filter must be 2 * prod(later rates) long"
+            wc, bc = ups_combined(subs, sd[f"dec.ups.{i}.bias"].float(), rate, (k - rate) // 2, wn.float(),
+                                  sd[f"dec.noise_convs.{i}.bias"].float(), sf_c)
+            put(f"dec.ups.{i}.comb.tc", pack_conv_tc_general(wc))
+            put(f"dec.ups.{i}.comb.b", bc)
         conv(f"dec.noise.{i}", wn, sd[f"dec.noise_convs.{i}.bias"])
         if wn.shape[-1] > 8:
             # long noise filter = Conv1d(1->C, K=2*sf, stride sf): on the source reshaped to sf "channels"
