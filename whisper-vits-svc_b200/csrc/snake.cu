@@ -88,7 +88,7 @@ constexpr int PF_RUNS = 256, PF_OUT_RUNS = PF_RUNS - 2, PF_MAXC = 16, PF_K = 7;
 
 struct PostTaps { float w[PF_MAXC][PF_K]; };
 
-__global__ void __launch_bounds__(PF_RUNS)
+__global__ void __launch_bounds__(PF_RUNS, 2)
 post_fused_kernel(const float* __restrict__ x, float* __restrict__ wave, const float* __restrict__ ea,
                   const float* __restrict__ inv_b, const SnakeTapsV tp, const PostTaps pw, int C, int L) {
   __shared__ __align__(16) float srow[2][PF_RUNS * 8];
