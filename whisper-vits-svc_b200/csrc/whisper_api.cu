@@ -13,6 +13,7 @@
 namespace svcb {
 int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
                    int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0);
+int launch_im2col_s1_image(const float* mel, void* img, int B, int n_mels, int n, cudaStream_t s);
 int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s);
 int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
                              cudaStream_t s);
@@ -31,7 +32,7 @@ struct WBlock {
 struct svcb_whisper {
   svcb_whisper_config cfg;
   std::map<std::string, std::pair<const float*, uint64_t>> tensors;
-  const float *conv1_w, *conv1_b, *conv2_wimg, *conv2_b, *pos, *lnp_g, *lnp_b;
+  const float *conv1_wimg, *conv1_b, *conv2_wimg, *conv2_b, *pos, *lnp_g, *lnp_b;
   std::vector<svcb::WBlock> blocks;
 };
 
@@ -49,7 +50,8 @@ static WLayout whisper_layout(const svcb_whisper_config& c, int B, int n) {
   L.M = B * L.n2;
   const size_t D = c.n_state;
   size_t off = 0;
-  L.h1 = off; off = align256(off + (size_t)B * D * n * 4);
+  // im2col tile image of the log-mel for conv1: [ceil(B n / 128)][K1p / 64][8][128][8] bf16, K1p = 3 n_mels padded to 64
+  L.h1 = off; off = align256(off + ((size_t)B * n + 127) / 128 * 128 * ((3 * (size_t)c.n_mels + 63) / 64 * 64) * 2);
   L.x = off; off = align256(off + (size_t)L.M * D * 4);
   const size_t Mp = (size_t)(L.M + 127) / 128 * 128;  // tile images are padded to whole 128-row tiles
   L.a = off; off = align256(off + Mp * D * 2);
@@ -98,7 +100,7 @@ int svcb_whisper_create(const void* dev_blob, size_t blob_bytes, const svcb_tens
     return it->second.first;
   };
   const uint64_t D = c.n_state;
-  w->conv1_w = get("conv1.w", (uint64_t)c.n_mels * 3 * D); w->conv1_b = get("conv1.b", D);
+  w->conv1_wimg = get("conv1.wimg", D * ((3 * (uint64_t)c.n_mels + 63) / 64 * 64) / 2); w->conv1_b = get("conv1.b", D);
   w->conv2_wimg = get("conv2.wimg", D * 3 * D / 2); w->conv2_b = get("conv2.b", D);
   w->pos = get("pos", (uint64_t)c.n_ctx * D);
   w->lnp_g = get("ln_post.g", D); w->lnp_b = get("ln_post.b", D);
@@ -134,22 +136,18 @@ int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int
   if (!ws || ((uintptr_t)ws & 255) || ws_bytes < L.total) { set_error("whisper workspace too small or misaligned"); return SVCB_E_WORKSPACE; }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   char* base = static_cast<char*>(ws);
-  float* h1 = reinterpret_cast<float*>(base + L.h1);
+  void* a1 = base + L.h1;
   float* x = reinterpret_cast<float*>(base + L.x);
   void* a = base + L.a; void* qkv = base + L.qkv; void* att = base + L.att; void* mid = base + L.mid;
   const int D = c.n_state, n = n_frames, n2 = L.n2, M = L.M;
-  {  // conv1 + GELU (whisper/model.py:149)
-    ConvParams p;
-    p.x = mel; p.sxb = (long long)c.n_mels * n; p.sxc = n; p.sxt = 1;
-    p.w = w->conv1_w; p.cout_pad = D; p.bias = w->conv1_b;
-    p.y = h1; p.syb = (long long)D * n; p.syc = n; p.syt = 1;
-    p.B = B; p.Cin = c.n_mels; p.Cout = D; p.Tin = n; p.K = 3; p.pad = 1; p.nq = n; p.act = ACT_GELU;
-    SVCB_TRY(launch_conv1d(p, s));
-  }
-  // conv2 (k=3, stride 2) + GELU + positional embedding, time-major (:150-157) as a tensor-core GEMM:
-  // im2col tile image of h1 (parked in the MLP hidden buffer, free until the first block) x the
-  // [D, 3D] weight image; the fp32 CUDA-core version of this layer was 25 % of the encoder's time
-  SVCB_TRY(launch_im2col_s2_image(h1, mid, B, D, n, n2, s));
+  // conv1 + GELU (whisper/model.py:149) as a tensor-core GEMM over the im2col image of the log-mel; its epilogue
+  // scatters GELU(h1) straight into conv2's im2col tile image (parked in the MLP hidden buffer, free until the first
+  // block), which is zeroed first: the t = -1 taps and the rows that pad M to whole tiles are never written.  (The fp32
+  // CUDA-core conv1 + the separate im2col pass were 2.0 of the encoder's 33.6 ms.)
+  SVCB_CUDA_CHECK(cudaMemsetAsync(mid, 0, (size_t)(M + 127) / 128 * 128 * 3 * D * 2, s));
+  SVCB_TRY(launch_im2col_s1_image(mel, a1, B, c.n_mels, n, s));
+  SVCB_TRY(launch_gemm_tc(a1, w->conv1_wimg, w->conv1_b, mid, nullptr, B * n, D, (3 * c.n_mels + 63) / 64 * 64, 5, s, n));
+  // conv2 (k=3, stride 2) + GELU + positional embedding, time-major (:150-157): im2col image x the [D, 3D] weight image
   SVCB_TRY(launch_gemm_tc(mid, w->conv2_wimg, w->conv2_b, x, w->pos, M, D, 3 * D, 3, s, n2));
   // pad positions of the head-major QKV buffer are read (times P = 0) but never written: keep them finite
   if (qkv_heads_tp(n2) != n2) SVCB_CUDA_CHECK(cudaMemsetAsync(qkv, 0, (size_t)B * qkv_heads_tp(n2) * 3 * D * 2, s));

@@ -208,9 +208,15 @@ template <bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                void* __restrict__ y, int M, int D, float eps) {
+  // bf16 output: the 8 rows of the block are staged in shared memory and leave as whole 128-byte lines of the tile
+  // image (8 rows x one 16-byte octet are contiguous there); lane-wise 8-byte stores into the image touched 16
+  // half-filled sectors per instruction and held the kernel at 2.2 TB/s
+  extern __shared__ __align__(16) uint8_t ln_stage[];
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (row >= M) return;
-  const float* xr = x + (size_t)row * D;
+  const bool live = row < M;
+  if (!OUT_BF16 && !live) return;
+  const float* xr = x + (size_t)(live ? row : M - 1) * D;
+  const int srow = (D + 8) * 2;   // bytes per staged row (+16: conflict-free 16-byte reads down a column of rows)
   constexpr int MAXV = 16;  // D <= 32*4*16 = 2048
   float4 v[MAXV];
   const int nv = D / 128;  // float4 per lane
@@ -244,12 +250,22 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       const float4 bt = *reinterpret_cast<const float4*>(beta + c0);
       const float o0 = (v[i].x - mean) * rstd * gm.x + bt.x, o1 = (v[i].y - mean) * rstd * gm.y + bt.y;
       const float o2 = (v[i].z - mean) * rstd * gm.z + bt.z, o3 = (v[i].w - mean) * rstd * gm.w + bt.w;
-      if (OUT_BF16) {  // GEMM tile image (A operand of the following linear layer)
+      if (OUT_BF16) {  // GEMM tile image (A operand of the following linear layer), through the staging rows
         uint2 pk = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
-        *reinterpret_cast<uint2*>(static_cast<__nv_bfloat16*>(y) + gemm_img_off(row, c0, D / 64)) = pk;
+        *reinterpret_cast<uint2*>(ln_stage + (size_t)(threadIdx.x >> 5) * srow + (size_t)c0 * 2) = pk;
       } else {
         *reinterpret_cast<float4*>(static_cast<float*>(y) + (size_t)row * D + c0) = make_float4(o0, o1, o2, o3);
       }
+    }
+  }
+  if (OUT_BF16) {
+    __syncthreads();
+    const int row0 = blockIdx.x * 8, noct = D / 8;
+    for (int idx = threadIdx.x; idx < noct * 8; idx += 256) {
+      const int o = idx >> 3, r = idx & 7;
+      if (row0 + r < M)
+        *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(y) + gemm_img_off(row0 + r, o * 8, D / 64)) =
+            *reinterpret_cast<const uint4*>(ln_stage + (size_t)r * srow + (size_t)o * 16);
     }
   }
 }
@@ -258,7 +274,7 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* 
                    cudaStream_t s) {
   if (D % 128 || D > 2048) { set_error("ln_rows: D must be a multiple of 128 and <= 2048"); return SVCB_E_UNSUPPORTED; }
   KernelScope ks("ln_rows", s, 8.0 * M * (double)D, (out_bf16 ? 6.0 : 8.0) * M * (double)D);
-  if (out_bf16) ln_rows_kernel<true><<<(M + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, M, D, 1e-5f);
+  if (out_bf16) ln_rows_kernel<true><<<(M + 7) / 8, 256, (size_t)8 * (D + 8) * 2, s>>>(x, gamma, beta, y, M, D, 1e-5f);
   else ln_rows_kernel<false><<<(M + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, M, D, 1e-5f);
   SVCB_LAUNCH_CHECK("ln_rows");
   return SVCB_OK;

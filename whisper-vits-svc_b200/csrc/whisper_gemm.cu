@@ -27,7 +27,11 @@ namespace svcb {
 // im2col image, with the positional embedding (period n_ctx rows) as the addend (whisper/model.py:150-157)
 // 4: bf16 out = acc + bias in the head-major QKV layout of the attention kernel (common.cuh qkv_heads_off;
 //    N = 3 D, rows are items of res_mod positions each; pad rows are zeroed by the caller once)
-enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3, EPI_QKV_HEADS = 4 };
+// 5: the stem's conv1 (rows = items x res_mod frames): GELU(acc + bias) scattered straight into conv2's im2col tile
+//    image A2[b * n2 + t2][j * N + co] = h1[b][co][2 t2 + j - 1] (frame t feeds (t/2, j=1) when even, ((t+1)/2, j=0)
+//    and ((t-1)/2, j=2) when odd) — no h1 tensor, no im2col pass; the caller zeroes the image once (t = -1 taps, pad rows)
+enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3, EPI_QKV_HEADS = 4,
+                     EPI_GELU_CONV2_IMG = 5 };
 
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 
@@ -130,7 +134,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-          if (EPI == EPI_GELU_ADD_F32) {
+          if (EPI == EPI_GELU_ADD_F32 || EPI == EPI_GELU_CONV2_IMG) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
           }
@@ -147,7 +151,24 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
               if (EPI == EPI_GELU_BF16_IMAGE) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
               h[j] = __float2bfloat16_rn(x);
             }
-            if (EPI == EPI_QKV_HEADS) {   // res_mod = positions per item; 16 columns = two octets of one head
+            if (EPI == EPI_GELU_CONV2_IMG) {
+              __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+              const int nfr = res_mod, n2 = (nfr - 1) / 2 + 1, KT2 = 3 * N / GM_BK;
+              const int bi = m / nfr, t = m - bi * nfr;
+              const uint4 q0 = *reinterpret_cast<const uint4*>(h), q1 = *reinterpret_cast<const uint4*>(h + 8);
+              if (t & 1) {
+                const int ta = (t + 1) >> 1, tb = (t - 1) >> 1;
+                if (ta < n2) {
+                  *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + ta, n0 + c0, KT2)) = q0;
+                  *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + ta, n0 + c0 + 8, KT2)) = q1;
+                }
+                *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + tb, 2 * N + n0 + c0, KT2)) = q0;
+                *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + tb, 2 * N + n0 + c0 + 8, KT2)) = q1;
+              } else {
+                *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + (t >> 1), N + n0 + c0, KT2)) = q0;
+                *reinterpret_cast<uint4*>(ob + img_off(bi * n2 + (t >> 1), N + n0 + c0 + 8, KT2)) = q1;
+              }
+            } else if (EPI == EPI_QKV_HEADS) {   // res_mod = positions per item; 16 columns = two octets of one head
               __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
               const int Dm = N / 3, n = n0 + c0;
               const int w = n / Dm, hd = (n - w * Dm) >> 6, d = n & 63;
@@ -204,6 +225,9 @@ int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void
     case EPI_BF16_ROWMAJOR: return launch_gemm_t<256, EPI_BF16_ROWMAJOR>(A, W, bias, out, res, M, N, K, 0, s);
     case EPI_GELU_BF16_IMAGE: return launch_gemm_t<256, EPI_GELU_BF16_IMAGE>(A, W, bias, out, res, M, N, K, 0, s);
     case EPI_RESID_F32: return launch_gemm_t<256, EPI_RESID_F32>(A, W, bias, out, res, M, N, K, 0, s);
+    case EPI_GELU_CONV2_IMG:
+      if (res_mod <= 0 || M % res_mod || N % GM_BK) { set_error("gemm_tc: epilogue 5 needs rows = items x res_mod frames"); return SVCB_E_BAD_SHAPE; }
+      return launch_gemm_t<256, EPI_GELU_CONV2_IMG>(A, W, bias, out, res, M, N, K, res_mod, s);
     case EPI_QKV_HEADS:
       if (res_mod <= 0 || M % res_mod || N % 192) { set_error("gemm_tc: epilogue 4 needs rows = items x res_mod, N = 3 x heads x 64"); return SVCB_E_BAD_SHAPE; }
       return launch_gemm_t<256, EPI_QKV_HEADS>(A, W, bias, out, res, M, N, K, res_mod, s);
@@ -245,6 +269,45 @@ im2col_s2_image_kernel(const float* __restrict__ h1, __nv_bfloat16* __restrict__
     for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(tile[kc * 8 + e][r]);
     *reinterpret_cast<uint4*>(dst + (size_t)(kc * 128 + r) * 8) = *reinterpret_cast<const uint4*>(h);
   }
+}
+
+// Stem conv1 (Conv1d(n_mels, D, k=3, pad 1), whisper/model.py:149) as a GEMM: the A tile image of ITS im2col matrix,
+// A[m = b*n + t][k = j*n_mels + ci] = mel[b][ci][t + j - 1], zero outside the sequence, for k >= 3 n_mels (K padded
+// to 64) and in the rows that pad M to whole tiles.  One CTA = one (row tile, k tile).
+__global__ void __launch_bounds__(256)
+im2col_s1_image_kernel(const float* __restrict__ mel, __nv_bfloat16* __restrict__ img, int nm, int n, int M, int KT) {
+  __shared__ float tile[64][129];
+  const int mt = blockIdx.x, kt = blockIdx.y, tid = threadIdx.x;
+  for (int idx = tid; idx < 64 * 128; idx += 256) {
+    const int cc = idx >> 7, r = idx & 127;
+    const int m = mt * 128 + r, k = kt * 64 + cc;
+    float v = 0.f;
+    if (m < M && k < 3 * nm) {
+      const int b = m / n, t1 = m - b * n;
+      const int j = k / nm, ci = k - j * nm;
+      const int t = t1 + j - 1;
+      if (t >= 0 && t < n) v = __ldg(mel + ((size_t)b * nm + ci) * n + t);
+    }
+    tile[cc][r] = v;
+  }
+  __syncthreads();
+  __nv_bfloat16* dst = img + ((size_t)mt * KT + kt) * (GM_BM * GM_BK);
+  for (int idx = tid; idx < 8 * 128; idx += 256) {
+    const int kc = idx >> 7, r = idx & 127;
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(tile[kc * 8 + e][r]);
+    *reinterpret_cast<uint4*>(dst + (size_t)(kc * 128 + r) * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int launch_im2col_s1_image(const float* mel, void* img, int B, int n_mels, int n, cudaStream_t s) {
+  const int M = B * n, KT = (3 * n_mels + 63) / 64;
+  dim3 grid((M + 127) / 128, KT);
+  KernelScope ks("im2col_s1_image", s, 0.0, (double)M * KT * 64 * 2 + 4.0 * B * n_mels * (double)n * 3);
+  im2col_s1_image_kernel<<<grid, 256, 0, s>>>(mel, static_cast<__nv_bfloat16*>(img), n_mels, n, M, KT);
+  SVCB_LAUNCH_CHECK("im2col_s1_image");
+  return SVCB_OK;
 }
 
 int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s) {

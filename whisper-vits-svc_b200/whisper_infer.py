@@ -67,7 +67,13 @@ def pack_whisper(ckpt: dict):
     def put(n, t):
         items.append((n, t.detach().float().contiguous()))
 
-    put("conv1.w", pack.pack_conv(sd["encoder.conv1.weight"].float()))
+    # conv1 (k=3, stride 1) as a GEMM over an im2col image of the log-mel: W1[co][j*n_mels + ci] = w[co][ci][j],
+    # K padded from 3 * n_mels to a multiple of 64
+    w1 = sd["encoder.conv1.weight"].float()
+    k1 = 3 * w1.shape[1]
+    w1p = torch.zeros(D, (k1 + 63) // 64 * 64)
+    w1p[:, :k1] = w1.permute(0, 2, 1).reshape(D, k1)
+    items.append(("conv1.wimg", _bf16_as_f32(w1p)))
     put("conv1.b", sd["encoder.conv1.bias"])
     # conv2 (k=3, stride 2) runs as a GEMM over an im2col image: W2[co][j*D + ci] = w[co][ci][j]
     items.append(("conv2.wimg", _bf16_as_f32(sd["encoder.conv2.weight"].float().permute(0, 2, 1).reshape(D, 3 * D))))
