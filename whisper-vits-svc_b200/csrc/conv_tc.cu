@@ -6,7 +6,7 @@
 // the tensor cores.
 //
 //   D[t, co] = sum_cc sum_tap  A_cc[t + tap*dil, :] . W[tap, cc][co, :]      M = 128, N = BN, K = KCH
-// * Input channels are processed in chunks of KCH (32 or 64).  Four producer warps gather one
+// * Input channels are processed in chunks of KCH (32 or 64).  Eight producer warps gather one
 //   chunk of x (fp32, any strides — the time-major PPG input included), apply the optional input
 //   mask and the conv's zero padding, split to bf16 hi/lo and write the K-major panel layout of
 //   tc.cuh into a 2-deep A ring (generic proxy -> fence.proxy.async -> mbarrier).
@@ -63,7 +63,7 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
   const long long len = p.lengths ? p.lengths[b] : (long long)1 << 60;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&a_full[i], 256); tc::mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < wst; ++i) { tc::mbar_init(&w_full[i], 1); tc::mbar_init(&w_empty[i], 1); }
     tc::mbar_init(&bar_acc, 1);
     tc::fence_barrier_init();
@@ -76,48 +76,63 @@ conv_tc_kernel(const ConvTcParams p, const int wst) {
   tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
 
-  if (warp < 4) {
-    // ---------------------------------------------------------------- A producers
+  if (warp < 4 || warp >= 6) {
+    // ---------------------------------------------------------------- A producers: the eight warps that run the
+    // epilogue later.  A thread fetches TWO items (16 scalar or 4 vector loads in flight) before it converts either:
+    // with four warps and one item at a time a chunk cost ~4 global-load latencies and the gather, not the MMAs,
+    // set the pace of every small convolution (profiles/r02_notes.md §9).
+    const int pid = warp < 4 ? tid : tid - 64;   // 0 .. 255
     const float* xb = p.x + (long long)b * p.sxb;
     const float* x2b = p.x2 ? p.x2 + (long long)b * p.sx2b : nullptr;
+    const int n_items = R * KC;
+    auto fetch = [&](int item, int cc, float (&v)[8]) {
+      const int r = item % R, kc = item / R;
+      const int tau = n0row + r;
+      const int c0 = cc * p.kch + kc * 8;
+      const bool row_ok = tau >= 0 && tau < p.Tin && (!(p.flags & CONV_IN_MASK) || tau < len);
+      if (row_ok && x2b && c0 >= p.cin1) {   // second input: channel-contiguous windows (unaligned)
+        const float* s2 = x2b + (long long)tau * p.sx2t + (c0 - p.cin1);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (c0 - p.cin1 + e < p.cin2) ? __ldg(s2 + e) : 0.f;
+      } else if (row_ok) {
+        if (p.sxc == 1 && c0 + 8 <= p.Cin) {  // channel-contiguous input: two 16-byte loads
+          const float4* s4 = reinterpret_cast<const float4*>(xb + (long long)tau * p.sxt + c0);
+          const float4 u0 = __ldg(s4), u1 = __ldg(s4 + 1);
+          v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 8; ++e)
+            v[e] = (c0 + e < p.Cin) ? __ldg(xb + (long long)(c0 + e) * p.sxc + (long long)tau * p.sxt) : 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+      }
+    };
+    auto put = [&](int item, uint8_t* Ah, uint8_t* Al, const float (&v)[8]) {
+      const int r = item % R, kc = item / R;
+      __align__(16) __nv_bfloat16 hi[8], lo[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        hi[e] = __float2bfloat16_rn(v[e]);
+        lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
+      }
+      *reinterpret_cast<uint4*>(Ah + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(hi);
+      if (nparts == 2)
+        *reinterpret_cast<uint4*>(Al + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(lo);
+    };
     for (int cc = 0; cc < ncc; ++cc) {
       const int buf = cc & 1;
       if (cc >= 2) tc::mbar_wait(&a_empty[buf], (uint32_t)(((cc >> 1) - 1) & 1));
       uint8_t* Ah = A0 + (size_t)buf * a_buf;
       uint8_t* Al = Ah + a_part;
-      for (int item = tid; item < R * KC; item += 128) {
-        const int r = item % R, kc = item / R;
-        const int tau = n0row + r;
-        const int c0 = cc * p.kch + kc * 8;
-        float v[8];
-        const bool row_ok = tau >= 0 && tau < p.Tin && (!(p.flags & CONV_IN_MASK) || tau < len);
-        if (row_ok && x2b && c0 >= p.cin1) {   // second input: channel-contiguous windows (unaligned)
-          const float* s2 = x2b + (long long)tau * p.sx2t + (c0 - p.cin1);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = (c0 - p.cin1 + e < p.cin2) ? __ldg(s2 + e) : 0.f;
-        } else if (row_ok) {
-          if (p.sxc == 1 && c0 + 8 <= p.Cin) {  // channel-contiguous input: two 16-byte loads
-            const float4* s4 = reinterpret_cast<const float4*>(xb + (long long)tau * p.sxt + c0);
-            const float4 u0 = __ldg(s4), u1 = __ldg(s4 + 1);
-            v[0] = u0.x; v[1] = u0.y; v[2] = u0.z; v[3] = u0.w; v[4] = u1.x; v[5] = u1.y; v[6] = u1.z; v[7] = u1.w;
-          } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e)
-              v[e] = (c0 + e < p.Cin) ? __ldg(xb + (long long)(c0 + e) * p.sxc + (long long)tau * p.sxt) : 0.f;
-          }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = 0.f;
-        }
-        __align__(16) __nv_bfloat16 hi[8], lo[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          hi[e] = __float2bfloat16_rn(v[e]);
-          lo[e] = __float2bfloat16_rn(v[e] - __bfloat162float(hi[e]));
-        }
-        *reinterpret_cast<uint4*>(Ah + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(hi);
-        if (nparts == 2)
-          *reinterpret_cast<uint4*>(Al + ((size_t)kc * R + r) * 16) = *reinterpret_cast<const uint4*>(lo);
+      for (int it0 = pid; it0 < n_items; it0 += 512) {
+        const int it1 = it0 + 256;
+        float va[8], vb[8];
+        fetch(it0, cc, va);
+        if (it1 < n_items) fetch(it1, cc, vb);
+        put(it0, Ah, Al, va);
+        if (it1 < n_items) put(it1, Ah, Al, vb);
       }
       tc::fence_proxy_async_smem();
       ct_arrive(&a_full[buf]);
