@@ -11,6 +11,7 @@ synthetic checkpoint through the loader surgery of whisper/inference.py:11-20 (d
 quarter of the encoder blocks deleted, strict=False load) and `model.encoder(mel)` is stored next to
 the mel; oracle/whisper_oracle.py must reproduce it.
 """
+import math
 import os
 import sys
 
@@ -141,6 +142,41 @@ def whisper_case(name):
     print(name, "ppg rms %.3f" % ppg.pow(2).mean().sqrt().item(), "oracle-vs-reference max abs", err)
 
 
+HUBERT_CASES = {  # name: (checkpoint seed, B, n_samples, input seed)
+    "hubert_soft_b2_n8000": (31, 2, 8000, 32),
+    "hubert_soft_b1_n16123": (33, 1, 16123, 34),
+}
+
+
+def hubert_wav(seed, B, n):
+    g = torch.Generator().manual_seed(seed)
+    t = torch.arange(n) / 16000.0
+    tone = 0.3 * torch.sin(2 * math.pi * 220.0 * t)[None, :] * (1.0 + 0.5 * torch.sin(2 * math.pi * 3.0 * t))[None, :]
+    return (tone + 0.1 * torch.randn(B, n, generator=g)).float().unsqueeze(1)
+
+
+def ref_hubert(sd):
+    """hubert/hubert_model.py:212-222 in effect (the state dict is passed in, not read from disk)."""
+    hm = ref_import.import_hubert_model()
+    model = hm.HubertSoft()
+    model.load_state_dict(sd)
+    return model.eval()
+
+
+def hubert_case(name):
+    from oracle import hubert_oracle as HO
+    ck_seed, B, n, in_seed = HUBERT_CASES[name]
+    sd = synth.hubert_checkpoint(ck_seed)
+    wav = hubert_wav(in_seed, B, n)
+    units = ref_hubert(sd).units(wav)
+    units_o = HO.units(sd, wav)
+    err = (units - units_o).abs().max().item()
+    assert err < 2e-5, f"hubert oracle != reference ({err})"
+    assert units.shape[1] == HO.frames(n)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), wav=wav.numpy(), units=units.numpy())
+    print(name, tuple(units.shape), "units rms %.3f" % units.pow(2).mean().sqrt().item(), "oracle-vs-reference max abs", err)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     hp = hparams.load_hparams(os.path.join(ROOT, "configs", "base.yaml"))
@@ -151,3 +187,5 @@ if __name__ == "__main__":
     gen_case("gen192_b1_t64", hp, seed=14, B=1, T=64)
     for name in WHISPER_CASES:
         whisper_case(name)
+    for name in HUBERT_CASES:
+        hubert_case(name)

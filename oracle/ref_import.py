@@ -86,6 +86,13 @@ def import_whisper_model():
     return wm
 
 
+def import_hubert_model():
+    """hubert/hubert_model.py (needs only torch)."""
+    _ensure_path()
+    import hubert.hubert_model as hm  # noqa
+    return hm
+
+
 @contextlib.contextmanager
 def record_rng(log: list):
     """Record every tensor returned by torch.randn_like / torch.rand inside the block."""

@@ -160,3 +160,40 @@ def test_whisper_oracle_matches_reference_live(over, B, n):
     got = wo.audio_encoder(ck, mel)
     assert got.shape == ref.shape == (B, (n - 1) // 2 + 1, over["n_audio_state"])
     assert max_abs(got, ref) <= 1e-6
+
+
+# ----------------------------------------------------------------------------- HuBERT-Soft
+HUBERT_GOLDEN = ["hubert_soft_b2_n8000", "hubert_soft_b1_n16123"]
+
+
+def _hubert_case(name):
+    from oracle import make_golden as mg
+    ck_seed, B, n, in_seed = mg.HUBERT_CASES[name]
+    return synth.hubert_checkpoint(ck_seed), mg.hubert_wav(in_seed, B, n)
+
+
+@pytest.mark.parametrize("name", HUBERT_GOLDEN)
+def test_hubert_oracle_matches_golden(name):
+    """tests/golden/hubert_*.npz are outputs of the unmodified reference `HubertSoft.units`
+    (oracle/make_golden.py:hubert_case); the restatement must reproduce them."""
+    from oracle import hubert_oracle as ho
+    g = _load(name)
+    sd, wav = _hubert_case(name)
+    assert np.array_equal(wav.numpy(), g["wav"])           # the input recipe is reproducible
+    got = ho.units(sd, wav)
+    assert got.shape == g["units"].shape == (wav.shape[0], ho.frames(wav.shape[-1]), 256)
+    assert max_abs(got, g["units"]) <= 2e-5
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_hubert_oracle_matches_reference_live():
+    """The pin itself: the reference's `HubertSoft()` with the synthetic state dict loaded (strict), `units(wav)`
+    (hubert/hubert_model.py:68-72) against `hubert_oracle.units` on the same state dict and audio."""
+    from oracle import hubert_oracle as ho, make_golden as mg
+    sd = synth.hubert_checkpoint(7)
+    wav = mg.hubert_wav(8, 1, 5003)
+    with torch.no_grad():
+        ref = mg.ref_hubert(sd).units(wav)
+    got = ho.units(sd, wav)
+    assert got.shape == ref.shape == (1, ho.frames(5003), 256)
+    assert max_abs(got, ref) <= 2e-5

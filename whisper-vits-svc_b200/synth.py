@@ -185,3 +185,47 @@ def whisper_checkpoint(dims: dict | None = None, seed: int = 1234, kept_layers: 
     sd["encoder.ln_post.weight"] = 1.0 + r.n(D, std=0.1)
     sd["encoder.ln_post.bias"] = r.n(D, std=0.1)
     return {"dims": dims, "model_state_dict": {k: v.float().contiguous() for k, v in sd.items()}}
+
+
+HUBERT_SOFT_DIMS = dict(conv_dim=512, d_model=768, n_head=12, d_ff=3072, n_layer=12, out_dim=256, pos_kernel=128, pos_groups=16)
+
+
+def hubert_checkpoint(seed: int = 1234, n_layer: int = 12):
+    """Synthetic HuBERT-Soft state dict in the reference's format (hubert/hubert_model.py:11-30,75-130: the keys
+    `hubert_soft()` loads, :212-222).  No pretrained weights exist in the container (hubert_pretrain/ holds a README)."""
+    r = _Gen(seed)
+    C, D, FF = 512, 768, 3072
+    sd: Dict[str, torch.Tensor] = {}
+    sd["masked_spec_embed"] = r.n(D, std=0.3)
+    sd["feature_extractor.conv0.weight"] = r.n(C, 1, 10, std=0.3)
+    sd["feature_extractor.norm0.weight"] = 1.0 + r.n(C, std=0.1)
+    sd["feature_extractor.norm0.bias"] = r.n(C, std=0.1)
+    for i, k in enumerate((3, 3, 3, 3, 2, 2), 1):
+        sd[f"feature_extractor.conv{i}.weight"] = r.n(C, C, k, std=1.4 / math.sqrt(C * k))
+    sd["feature_projection.norm.weight"] = 1.0 + r.n(C, std=0.1)
+    sd["feature_projection.norm.bias"] = r.n(C, std=0.1)
+    sd["feature_projection.projection.weight"] = r.n(D, C, std=1.0 / math.sqrt(C))
+    sd["feature_projection.projection.bias"] = r.n(D, std=0.05)
+    v = r.n(D, 48, 128, std=1.0 / math.sqrt(48 * 128))
+    sd["positional_embedding.conv.weight_v"] = v
+    sd["positional_embedding.conv.weight_g"] = v.pow(2).sum((0, 1), keepdim=True).sqrt() * (1.0 + r.n(1, 1, 128, std=0.1))
+    sd["positional_embedding.conv.bias"] = r.n(D, std=0.05)
+    sd["norm.weight"] = 1.0 + r.n(D, std=0.1)
+    sd["norm.bias"] = r.n(D, std=0.1)
+    for i in range(n_layer):
+        b = f"encoder.layers.{i}"
+        sd[f"{b}.self_attn.in_proj_weight"] = r.n(3 * D, D, std=0.8 / math.sqrt(D))
+        sd[f"{b}.self_attn.in_proj_bias"] = r.n(3 * D, std=0.05)
+        sd[f"{b}.self_attn.out_proj.weight"] = r.n(D, D, std=0.8 / math.sqrt(D))
+        sd[f"{b}.self_attn.out_proj.bias"] = r.n(D, std=0.05)
+        sd[f"{b}.linear1.weight"] = r.n(FF, D, std=1.0 / math.sqrt(D))
+        sd[f"{b}.linear1.bias"] = r.n(FF, std=0.05)
+        sd[f"{b}.linear2.weight"] = r.n(D, FF, std=0.5 / math.sqrt(FF))
+        sd[f"{b}.linear2.bias"] = r.n(D, std=0.05)
+        for nm in ("norm1", "norm2"):
+            sd[f"{b}.{nm}.weight"] = 1.0 + r.n(D, std=0.1)
+            sd[f"{b}.{nm}.bias"] = r.n(D, std=0.1)
+    sd["proj.weight"] = r.n(256, D, std=1.0 / math.sqrt(D))
+    sd["proj.bias"] = r.n(256, std=0.05)
+    sd["label_embedding.weight"] = r.n(100, 256, std=1.0)
+    return {k: v.float().contiguous() for k, v in sd.items()}
