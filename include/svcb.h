@@ -169,6 +169,23 @@ size_t svcb_whisper_workspace_bytes(const svcb_whisper* w, int32_t B, int32_t n_
 int svcb_whisper_encode(const svcb_whisper* w, const float* mel, float* out, int32_t B, int32_t n_frames,
                         void* ws, size_t ws_bytes, svcb_stream stream);
 
+/* ------------------------------------------------------------------ content encoder (HuBERT-Soft) */
+typedef struct svcb_hubert svcb_hubert;
+/* Replaces hubert.inference.load_model / hubert_model.hubert_soft (hubert/inference.py:17-23, hubert_model.py:212-222).
+ * Blob names/layouts: whisper-vits-svc_b200/hubert_infer.py:pack_hubert (linear weights as bf16 tile images, the
+ * convolutional stem and the grouped positional conv fp32).  n_layer = transformer layers in the blob (12). */
+int svcb_hubert_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host, int32_t n_entries,
+                       int32_t n_layer, svcb_hubert** out);
+void svcb_hubert_destroy(svcb_hubert* h);
+/* frames produced for n_samples of 16 kHz audio (pad 40 + 40, k10 s5, then six stride-2 convs): ~ n_samples / 320 */
+int32_t svcb_hubert_frames(int32_t n_samples);
+size_t svcb_hubert_workspace_bytes(const svcb_hubert* h, int32_t B, int32_t n_samples);
+/* Replaces HubertSoft.units (hubert/hubert_model.py:68-72): wav [B, n_samples] fp32 (16 kHz, equal-length chunks) ->
+ * out [B, svcb_hubert_frames(n_samples), 256] fp32.  taps: null, or 5 device pointers (each may be null) that receive
+ * the time-major intermediates [B*T, 512 | 768]: 0 features, 1 projected, 2 embedded, 3 after layer 0, 4 encoded. */
+int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_t B, int32_t n_samples, void* ws,
+                      size_t ws_bytes, float* const* taps, svcb_stream stream);
+
 /* Replaces whisper.audio.log_mel_spectrogram (whisper/audio.py:68-100) plus the extractor's mel noise
  * (whisper/inference.py:46,58) for B equal-length chunks of 16 kHz audio already on the device:
  * audio [B, n_samples] fp32 -> mel [B, n_mels, n_samples/160] fp32 (Hann STFT 400/160, reflect-centred,

@@ -79,6 +79,11 @@ SIGNATURES = {
     "svcb_whisper_destroy": (None, [c_void_p]),
     "svcb_whisper_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
     "svcb_whisper_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "svcb_hubert_create": (c_int, [c_void_p, c_size_t, POINTER(TensorEntry), c_int32, c_int32, POINTER(c_void_p)]),
+    "svcb_hubert_destroy": (None, [c_void_p]),
+    "svcb_hubert_frames": (c_int32, [c_int32]),
+    "svcb_hubert_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "svcb_hubert_units": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]),
     "svcb_whisper_log_mel": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "svcb_op_gemm_bf16_scratch_bytes": (c_size_t, [c_int32] * 3),
     "svcb_op_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p, c_size_t, c_void_p]),

@@ -1,0 +1,256 @@
+// HuBERT-Soft content encoder (the `vec` input of the SVC model, 256-d at 50 frames/s) — SURVEY.md §8f-2.
+//
+// Replaces HubertSoft.units (hubert/hubert_model.py:64-72 -> encode :39-48):
+//   pad 40 + 40 -> FeatureExtractor (:75-95: Conv1d(1,512,10,5) -> GroupNorm(512,512) -> GELU, six stride-2 convs + GELU)
+//   -> FeatureProjection (:98-109: LayerNorm(512) -> Linear(512,768)) -> x + GELU(pos_conv(x)[..., :-1]) (:112-128:
+//   Conv1d(768,768,128, pad 64, groups 16), weight_norm folded by the packer) -> LayerNorm(768) -> 12 x
+//   nn.TransformerEncoderLayer(768, 12, 3072, gelu, post-LN) (:131-153) -> Linear(768,256).
+// The transformer runs on the PPG extractor's kernels: tcgen05 GEMMs over bf16 tile images (whisper_gemm.cu), the
+// tcgen05 attention with P in tensor memory (whisper_attn_tc.cu: 12 heads of 64, scores / 8), `ln_rows` writing the
+// normalised rows both as the next GEMM's A image and as the fp32 residual stream (post-LN).  The convolutional stem
+// runs in fp32 on the CUDA cores (`conv1d`; 97 GFLOP per 20 s chunk — the tensor-core im2col form of the Whisper stem
+// is the next step), the last conv writing time-major rows through its output strides; GroupNorm is one CTA per
+// (item, channel) row.
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace svcb {
+int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0);
+int launch_whisper_attention_tc(const void* qkv_img, void* out_img, int B, int T, int D, int heads, int vswap, cudaStream_t s);
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
+                   cudaStream_t s, float* y32 = nullptr);
+
+constexpr int HB_C = 512, HB_D = 768, HB_H = 12, HB_FF = 3072, HB_OUT = 256, HB_PK = 128, HB_PG = 16, HB_PHALF = 24;
+static const int kHbKernels[6] = {3, 3, 3, 3, 2, 2};
+
+struct HLayer {
+  const float *wqkv, *bqkv, *wo, *bo, *w1, *b1, *w2, *b2, *ln1g, *ln1b, *ln2g, *ln2b;
+};
+
+// GroupNorm(512, 512) = per-(item, channel) normalisation over time, affine, then GELU; in place on [rows][T]
+__global__ void __launch_bounds__(256)
+groupnorm_gelu_rows_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta, int C,
+                           int T, float eps) {
+  __shared__ float red[8];
+  const int row = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* xr = x + (size_t)row * T;
+  auto block_sum = [&](float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += red[i];
+    return s;
+  };
+  float s = 0.f;
+  for (int t = tid; t < T; t += 256) s += xr[t];
+  const float mean = block_sum(s) / (float)T;
+  float q = 0.f;
+  for (int t = tid; t < T; t += 256) { const float d = xr[t] - mean; q += d * d; }
+  const float rstd = rsqrtf(block_sum(q) / (float)T + eps);
+  const float g = __ldg(gamma + row % C) * rstd, b = __ldg(beta + row % C);
+  for (int t = tid; t < T; t += 256) {
+    const float v = (xr[t] - mean) * g + b;
+    xr[t] = 0.5f * v * (1.f + erff(v * 0.70710678118654752440f));
+  }
+}
+
+static size_t align256h(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct HLayout {
+  int T[7];            // frames after conv0 .. conv6
+  int M;
+  size_t bufa, bufb, rows, a512, x, y, a, qkv, att, mid, total;
+};
+static HLayout hubert_layout(int B, int n_samples) {
+  HLayout L;
+  L.T[0] = (n_samples + 80 - 10) / 5 + 1;
+  for (int i = 1; i <= 6; ++i) L.T[i] = L.T[i - 1] >= kHbKernels[i - 1] ? (L.T[i - 1] - kHbKernels[i - 1]) / 2 + 1 : 0;
+  const int T = L.T[6];
+  L.M = B * T;
+  const size_t Mp = ((size_t)L.M + 127) / 128 * 128;
+  size_t off = 0;
+  L.bufa = off; off = align256h(off + (size_t)B * HB_C * L.T[0] * 4);
+  L.bufb = off; off = align256h(off + (size_t)B * HB_C * (L.T[1] > 0 ? L.T[1] : 1) * 4);
+  L.rows = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_C * 4);
+  L.a512 = off; off = align256h(off + Mp * HB_C * 2);
+  L.x = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_D * 4);
+  L.y = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_D * 4);
+  L.a = off; off = align256h(off + Mp * HB_D * 2);
+  L.qkv = off; off = align256h(off + (size_t)B * qkv_heads_tp(T > 0 ? T : 1) * 3 * HB_D * 2);
+  L.att = off; off = align256h(off + Mp * HB_D * 2);
+  L.mid = off; off = align256h(off + Mp * HB_FF * 2);
+  L.total = off + 4096;
+  return L;
+}
+
+}  // namespace svcb
+
+using namespace svcb;
+
+struct svcb_hubert {
+  int n_layer = 0;
+  std::map<std::string, std::pair<const float*, uint64_t>> tensors;
+  const float *conv0_w, *gn_g, *gn_b, *conv_w[6], *fp_lng, *fp_lnb, *fp_w, *fp_b, *pos_w[HB_PG][2], *pos_b, *norm_g, *norm_b,
+      *proj_w, *proj_b;
+  std::vector<HLayer> layers;
+};
+
+extern "C" {
+
+int svcb_hubert_create(const void* dev_blob, size_t blob_bytes, const svcb_tensor_entry* table_host, int32_t n_entries,
+                       int32_t n_layer, svcb_hubert** out) {
+  if (!dev_blob || !table_host || !out || n_layer < 1 || n_layer > 64) { set_error("svcb_hubert_create: bad argument"); return SVCB_E_BAD_SHAPE; }
+  if (((uintptr_t)dev_blob & 255) != 0) { set_error("weight blob must be 256-byte aligned"); return SVCB_E_BAD_ALIGN; }
+  int dev = 0;
+  SVCB_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  SVCB_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) { set_error("libsvc_b200 is built for sm_100a only"); return SVCB_E_UNSUPPORTED; }
+  svcb_hubert* h = new svcb_hubert();
+  h->n_layer = n_layer;
+  const char* blob = static_cast<const char*>(dev_blob);
+  for (int i = 0; i < n_entries; ++i) {
+    const svcb_tensor_entry& e = table_host[i];
+    if (e.offset_bytes % 256 != 0 || e.offset_bytes + e.numel * sizeof(float) > blob_bytes) {
+      set_error(std::string("bad table entry: ") + e.name);
+      delete h;
+      return SVCB_E_BAD_ALIGN;
+    }
+    h->tensors[std::string(e.name, strnlen(e.name, sizeof(e.name)))] = {reinterpret_cast<const float*>(blob + e.offset_bytes), e.numel};
+  }
+  bool ok = true;
+  std::string missing;
+  auto get = [&](const std::string& n, uint64_t min_numel) -> const float* {
+    auto it = h->tensors.find(n);
+    if (it == h->tensors.end() || it->second.second < min_numel) { if (ok) missing = n; ok = false; return nullptr; }
+    return it->second.first;
+  };
+  const uint64_t C = HB_C, D = HB_D, FF = HB_FF;
+  h->conv0_w = get("fe.conv0.w", 10 * C);
+  h->gn_g = get("fe.gn.g", C); h->gn_b = get("fe.gn.b", C);
+  for (int i = 0; i < 6; ++i) h->conv_w[i] = get("fe.conv" + std::to_string(i + 1) + ".w", C * kHbKernels[i] * C);
+  h->fp_lng = get("fp.ln.g", C); h->fp_lnb = get("fp.ln.b", C);
+  h->fp_w = get("fp.w", D * C / 2); h->fp_b = get("fp.b", D);
+  for (int g = 0; g < HB_PG; ++g)
+    for (int hf = 0; hf < 2; ++hf)
+      h->pos_w[g][hf] = get("pos." + std::to_string(g) + "." + std::to_string(hf) + ".w", (uint64_t)(D / HB_PG) * HB_PK * HB_PHALF);
+  h->pos_b = get("pos.b", D);
+  h->norm_g = get("norm.g", D); h->norm_b = get("norm.b", D);
+  h->layers.resize(n_layer);
+  for (int i = 0; i < n_layer; ++i) {
+    const std::string p = "L" + std::to_string(i);
+    HLayer& l = h->layers[i];
+    l.wqkv = get(p + ".wqkv", 3 * D * D / 2); l.bqkv = get(p + ".bqkv", 3 * D);
+    l.wo = get(p + ".wo", D * D / 2); l.bo = get(p + ".bo", D);
+    l.w1 = get(p + ".w1", FF * D / 2); l.b1 = get(p + ".b1", FF);
+    l.w2 = get(p + ".w2", FF * D / 2); l.b2 = get(p + ".b2", D);
+    l.ln1g = get(p + ".ln1.g", D); l.ln1b = get(p + ".ln1.b", D);
+    l.ln2g = get(p + ".ln2.g", D); l.ln2b = get(p + ".ln2.b", D);
+  }
+  h->proj_w = get("proj.w", (uint64_t)HB_OUT * D / 2); h->proj_b = get("proj.b", HB_OUT);
+  if (!ok) { set_error("tensor missing or too small in hubert blob: " + missing); delete h; return SVCB_E_MISSING_TENSOR; }
+  *out = h;
+  return SVCB_OK;
+}
+
+void svcb_hubert_destroy(svcb_hubert* h) { delete h; }
+
+int32_t svcb_hubert_frames(int32_t n_samples) { return n_samples > 0 ? hubert_layout(1, n_samples).T[6] : 0; }
+
+size_t svcb_hubert_workspace_bytes(const svcb_hubert* h, int32_t B, int32_t n_samples) {
+  if (!h || B <= 0 || n_samples <= 0) return 0;
+  return hubert_layout(B, n_samples).total;
+}
+
+int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_t B, int32_t n_samples, void* ws,
+                      size_t ws_bytes, float* const* taps, svcb_stream stream) {
+  if (!h || !wav || !out || B <= 0 || n_samples <= 0) { set_error("svcb_hubert_units: bad argument"); return SVCB_E_BAD_SHAPE; }
+  const HLayout L = hubert_layout(B, n_samples);
+  const int T = L.T[6], M = L.M;
+  if (T < 1) { set_error("svcb_hubert_units: audio shorter than one frame"); return SVCB_E_BAD_SHAPE; }
+  if (!ws || ((uintptr_t)ws & 255) || ws_bytes < L.total) { set_error("hubert workspace too small or misaligned"); return SVCB_E_WORKSPACE; }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  char* base = static_cast<char*>(ws);
+  float* bufa = reinterpret_cast<float*>(base + L.bufa);
+  float* bufb = reinterpret_cast<float*>(base + L.bufb);
+  float* rows = reinterpret_cast<float*>(base + L.rows);
+  float* x = reinterpret_cast<float*>(base + L.x);
+  float* y = reinterpret_cast<float*>(base + L.y);
+  void* a512 = base + L.a512; void* a = base + L.a; void* qkv = base + L.qkv; void* att = base + L.att; void* mid = base + L.mid;
+  auto tap = [&](int i, const float* src, size_t n) -> int {
+    if (taps && taps[i]) SVCB_CUDA_CHECK(cudaMemcpyAsync(taps[i], src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    return SVCB_OK;
+  };
+  {  // conv0 over the zero-padded audio (pad 40 + 40, hubert_model.py:70) -> [B, 512, T0]
+    ConvParams p;
+    p.x = wav; p.sxb = n_samples; p.sxc = n_samples; p.sxt = 1;
+    p.w = h->conv0_w; p.cout_pad = HB_C; p.bias = nullptr;
+    p.y = bufa; p.syb = (long long)HB_C * L.T[0]; p.syc = L.T[0]; p.syt = 1;
+    p.B = B; p.Cin = 1; p.Cout = HB_C; p.Tin = n_samples; p.K = 10; p.stride = 5; p.pad = 40; p.nq = L.T[0];
+    SVCB_TRY(launch_conv1d(p, s));
+  }
+  {
+    KernelScope ks("groupnorm_gelu_rows", s, 0.0, 16.0 * B * HB_C * (double)L.T[0]);
+    groupnorm_gelu_rows_kernel<<<B * HB_C, 256, 0, s>>>(bufa, h->gn_g, h->gn_b, HB_C, L.T[0], 1e-5f);
+    SVCB_LAUNCH_CHECK("groupnorm_gelu_rows");
+  }
+  const float* cur = bufa;
+  for (int i = 1; i <= 6; ++i) {   // conv1 .. conv6 + GELU; the last one writes time-major rows [B * T, 512]
+    float* dst = i == 6 ? rows : (cur == bufa ? bufb : bufa);
+    ConvParams p;
+    p.x = cur; p.sxb = (long long)HB_C * L.T[i - 1]; p.sxc = L.T[i - 1]; p.sxt = 1;
+    p.w = h->conv_w[i - 1]; p.cout_pad = HB_C; p.bias = nullptr;
+    p.y = dst;
+    if (i == 6) { p.syb = (long long)T * HB_C; p.syc = 1; p.syt = HB_C; }
+    else { p.syb = (long long)HB_C * L.T[i]; p.syc = L.T[i]; p.syt = 1; }
+    p.B = B; p.Cin = HB_C; p.Cout = HB_C; p.Tin = L.T[i - 1]; p.K = kHbKernels[i - 1]; p.stride = 2; p.pad = 0; p.nq = L.T[i];
+    p.act = ACT_GELU;
+    SVCB_TRY(launch_conv1d(p, s));
+    cur = dst;
+  }
+  SVCB_TRY(tap(0, rows, (size_t)M * HB_C));
+  // FeatureProjection: LayerNorm(512) -> Linear(512, 768)
+  SVCB_TRY(launch_ln_rows(rows, h->fp_lng, h->fp_lnb, a512, M, HB_C, true, s));
+  SVCB_TRY(launch_gemm_tc(a512, h->fp_w, h->fp_b, x, nullptr, M, HB_D, HB_C, 2, s));
+  SVCB_TRY(tap(1, x, (size_t)M * HB_D));
+  // y = x + GELU(pos_conv(x)[..., :-1]): 16 groups of 48 channels, 128 taps, two 24-channel halves per group
+  for (int g = 0; g < HB_PG; ++g)
+    for (int hf = 0; hf < 2; ++hf) {
+      const int ci0 = g * (HB_D / HB_PG), co0 = ci0 + hf * HB_PHALF;
+      ConvParams p;
+      p.x = x + ci0; p.sxb = (long long)T * HB_D; p.sxc = 1; p.sxt = HB_D;
+      p.w = h->pos_w[g][hf]; p.cout_pad = HB_PHALF; p.bias = h->pos_b + co0;
+      p.y = y + co0; p.syb = (long long)T * HB_D; p.syc = 1; p.syt = HB_D;
+      p.res = x + co0;
+      p.B = B; p.Cin = HB_D / HB_PG; p.Cout = HB_PHALF; p.Tin = T; p.K = HB_PK; p.stride = 1; p.pad = HB_PK / 2; p.nq = T;
+      p.act = ACT_GELU;
+      SVCB_TRY(launch_conv1d(p, s));
+    }
+  SVCB_TRY(launch_ln_rows(y, h->norm_g, h->norm_b, a, M, HB_D, true, s, x));
+  SVCB_TRY(tap(2, x, (size_t)M * HB_D));
+  if (qkv_heads_tp(T) != T) SVCB_CUDA_CHECK(cudaMemsetAsync(qkv, 0, (size_t)B * qkv_heads_tp(T) * 3 * HB_D * 2, s));
+  for (int i = 0; i < h->n_layer; ++i) {   // post-LN layers: x = LN1(x + SA(x)); x = LN2(x + W2 gelu(W1 x))
+    const HLayer& l = h->layers[i];
+    SVCB_TRY(launch_gemm_tc(a, l.wqkv, l.bqkv, qkv, nullptr, M, 3 * HB_D, HB_D, 4, s, T));
+    SVCB_TRY(launch_whisper_attention_tc(qkv, att, B, T, HB_D, HB_H, 0, s));
+    SVCB_TRY(launch_gemm_tc(att, l.wo, l.bo, y, x, M, HB_D, HB_D, 2, s));
+    SVCB_TRY(launch_ln_rows(y, l.ln1g, l.ln1b, a, M, HB_D, true, s, x));
+    SVCB_TRY(launch_gemm_tc(a, l.w1, l.b1, mid, nullptr, M, HB_FF, HB_D, 1, s));
+    SVCB_TRY(launch_gemm_tc(mid, l.w2, l.b2, y, x, M, HB_D, HB_FF, 2, s));
+    SVCB_TRY(launch_ln_rows(y, l.ln2g, l.ln2b, a, M, HB_D, true, s, x));
+    if (i == 0) SVCB_TRY(tap(3, x, (size_t)M * HB_D));
+  }
+  SVCB_TRY(tap(4, x, (size_t)M * HB_D));
+  return launch_gemm_tc(a, h->proj_w, h->proj_b, out, nullptr, M, HB_OUT, HB_D, 2, s);
+}
+
+}  // extern "C"

@@ -22,7 +22,7 @@ int launch_image_to_rowmajor(const void* src, void* dst, int R, int K, cudaStrea
 int launch_qkv_rowmajor_to_heads(const void* src, void* dst, int B, int T, int D, cudaStream_t s);
 int launch_whisper_attention_tc(const void* qkv_img, void* out_img, int B, int T, int D, int heads, int vswap, cudaStream_t s);
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
-                   cudaStream_t s);
+                   cudaStream_t s, float* y32 = nullptr);
 struct WBlock {
   const float *ln1g, *ln1b, *ln2g, *ln2b, *bqkv, *bo, *b1, *b2;
   const void *wqkv, *wo, *w1, *w2;

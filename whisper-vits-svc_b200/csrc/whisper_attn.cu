@@ -207,7 +207,7 @@ int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T,
 template <bool OUT_BF16>
 __global__ void __launch_bounds__(256)
 ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-               void* __restrict__ y, int M, int D, float eps) {
+               void* __restrict__ y, float* __restrict__ y32, int M, int D, float eps) {
   // bf16 output: the 8 rows of the block are staged in shared memory and leave as whole 128-byte lines of the tile
   // image (8 rows x one 16-byte octet are contiguous there); lane-wise 8-byte stores into the image touched 16
   // half-filled sectors per instruction and held the kernel at 2.2 TB/s
@@ -251,6 +251,8 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
       const float o0 = (v[i].x - mean) * rstd * gm.x + bt.x, o1 = (v[i].y - mean) * rstd * gm.y + bt.y;
       const float o2 = (v[i].z - mean) * rstd * gm.z + bt.z, o3 = (v[i].w - mean) * rstd * gm.w + bt.w;
       if (OUT_BF16) {  // GEMM tile image (A operand of the following linear layer), through the staging rows
+        // (+ the fp32 rows when the normalised values are also the residual stream: post-LN layers, HuBERT)
+        if (y32 && live) *reinterpret_cast<float4*>(y32 + (size_t)row * D + c0) = make_float4(o0, o1, o2, o3);
         uint2 pk = make_uint2(pack_bf16(o0, o1), pack_bf16(o2, o3));
         *reinterpret_cast<uint2*>(ln_stage + (size_t)(threadIdx.x >> 5) * srow + (size_t)c0 * 2) = pk;
       } else {
@@ -270,12 +272,13 @@ ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, con
   }
 }
 
+// y32 (bf16 mode only, a buffer other than x): the same normalised rows in fp32 [M, D]
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
-                   cudaStream_t s) {
+                   cudaStream_t s, float* y32) {
   if (D % 128 || D > 2048) { set_error("ln_rows: D must be a multiple of 128 and <= 2048"); return SVCB_E_UNSUPPORTED; }
-  KernelScope ks("ln_rows", s, 8.0 * M * (double)D, (out_bf16 ? 6.0 : 8.0) * M * (double)D);
-  if (out_bf16) ln_rows_kernel<true><<<(M + 7) / 8, 256, (size_t)8 * (D + 8) * 2, s>>>(x, gamma, beta, y, M, D, 1e-5f);
-  else ln_rows_kernel<false><<<(M + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, M, D, 1e-5f);
+  KernelScope ks("ln_rows", s, 8.0 * M * (double)D, (out_bf16 ? (y32 ? 10.0 : 6.0) : 8.0) * M * (double)D);
+  if (out_bf16) ln_rows_kernel<true><<<(M + 7) / 8, 256, (size_t)8 * (D + 8) * 2, s>>>(x, gamma, beta, y, y32, M, D, 1e-5f);
+  else ln_rows_kernel<false><<<(M + 7) / 8, 256, 0, s>>>(x, gamma, beta, y, nullptr, M, D, 1e-5f);
   SVCB_LAUNCH_CHECK("ln_rows");
   return SVCB_OK;
 }

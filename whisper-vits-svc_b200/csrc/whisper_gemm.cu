@@ -123,7 +123,9 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
         uint32_t v[16];
         tc::tmem_ld16(tbase + (uint32_t)c0, v);
         float r16[16];
-        if ((EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) && m < M) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r16[j] = 0.f;
+        if ((EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) && m < M && res) {   // (EPI_RESID_F32 without res: plain fp32 output)
           const int mr = (EPI == EPI_GELU_ADD_F32 && res_mod > 0) ? m % res_mod : m;
           const float4* rr = reinterpret_cast<const float4*>(res + (size_t)mr * N + n0 + c0);
 #pragma unroll
