@@ -7,10 +7,10 @@ checkpoint and re-spawning the HuBERT / pitch extractors every time.  Here the m
 once per GPU, files are sharded across the ranks of a `torchrun` launch (one process per GPU, one
 NCCL broadcast of the packed weights, no collective on the data path), and per rank the chunks of ALL its
 files are bucketed by length and run as full device batches (hostio.BatchEngine) while host threads read
-features and write WAVs.  HuBERT / CREPE are outside the B200 hot path: `<name>.vec.npy` and
-`<name>.pit.csv` must sit next to `<name>.wav` (or in --feat); a file without them is reported and
-skipped — the reference would silently produce nothing for it either (subprocess exit codes are
-ignored there).
+features and write WAVs.  Missing `<name>.ppg.npy` / `<name>.vec.npy` are extracted in-process by the B200 Whisper /
+HuBERT-Soft encoders (one model load per rank).  CREPE is outside the B200 hot path:
+`<name>.pit.csv` must sit next to `<name>.wav` (or in --feat); a file without it is reported and skipped — the
+reference would silently produce nothing for it either (subprocess exit codes are ignored there).
 
     python svc_inference_batch.py --config configs/base.yaml --model sovits5.0.pth --wave waves/ --spk singer.npy
     python -m torch.distributed.run --nproc-per-node 8 svc_inference_batch.py ...   # 8 GPUs
@@ -38,6 +38,7 @@ def main():
     parser.add_argument('--shift', type=int, default=0, help="Pitch shift key.")
     parser.add_argument('--feat', type=str, default=None, help="dir holding <name>.{ppg,vec}.npy / .pit.csv")
     parser.add_argument('--whisper', type=str, default=os.path.join("whisper_pretrain", "large-v2.pt"))
+    parser.add_argument('--hubert', type=str, default=os.path.join("hubert_pretrain", "hubert-soft-0d54a1f4.pt"))
     parser.add_argument('--max-batch', type=int, default=32, help="chunks per device call (equal-length chunks of all files)")
     args = parser.parse_args()
     wave_path = args.wave
@@ -75,10 +76,12 @@ def main():
         name = waves[i]
         stem = os.path.join(feat, name[:-4])
         ppg_p, vec_p, pit_p = stem + ".ppg.npy", stem + ".vec.npy", stem + ".pit.csv"
-        if not (os.path.isfile(vec_p) and os.path.isfile(pit_p)):
-            raise FileNotFoundError(f"{vec_p} / {pit_p} missing (HuBERT and CREPE extractors are out of scope)")
+        if not os.path.isfile(pit_p):
+            raise FileNotFoundError(f"{pit_p} missing (the CREPE pitch extractor is out of scope)")
         if not os.path.isfile(ppg_p):
-            ppg_p = os.path.join(out_path, name + ".ppg.npy")     # written by the PPG pass below
+            ppg_p = os.path.join(out_path, name + ".ppg.npy")     # written by the extractor pass below
+        if not os.path.isfile(vec_p):
+            vec_p = os.path.join(out_path, name + ".vec.npy")
         ppg, vec, pit = hostio.prepare_features(ppg_p, vec_p, pit_p, args.shift)
         return name, spk, pit, ppg, vec
 
@@ -94,6 +97,18 @@ def main():
             except Exception as e:
                 print(f"[rank {rank}] {name}: PPG extraction FAILED {e}")
     del whisper
+    hubert = None
+    for i in mine:   # the same for the HuBERT-Soft units (svc_inference.py:144-148 of the reference)
+        name = waves[i]
+        if not os.path.isfile(os.path.join(feat, name[:-4] + ".vec.npy")):
+            try:
+                from whisper_vits_svc_b200 import hubert_infer
+                if hubert is None:
+                    hubert = hubert_infer.load_model(args.hubert, device)
+                hubert_infer.pred_vec(hubert, os.path.join(wave_path, name), os.path.join(out_path, name + ".vec.npy"))
+            except Exception as e:
+                print(f"[rank {rank}] {name}: HuBERT extraction FAILED {e}")
+    del hubert
 
     from concurrent.futures import ThreadPoolExecutor
     engine = hostio.BatchEngine(model, hp, device, max_batch=args.max_batch)
