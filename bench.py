@@ -13,10 +13,11 @@ weights exist offline), synthetic inputs per SURVEY.md §8d.
           (H2D of ppg/vec/pit/spk/lengths and D2H of the waveform inside the timed region)
   roofline / cpu_baseline : see DESIGN.md §Measurement
 
-The same JSON line carries two sub-records under "configs" (N=1 only) so that every BASELINE
+The same JSON line carries three sub-records under "configs" (N=1 only) so that every BASELINE
 configuration is visible to a driver that only runs `python bench.py --gpus N`:
   configs.generator : BASELINE configs[1]  NSF-BigVGAN generator forward, 80-ch x 864 latent, batch 8, 24 kHz label
   configs.whisper   : BASELINE configs[2]  truncated Whisper large-v2 encoder, 16 x 30 s log-mel
+  configs.hubert    : SURVEY 8f-2 (no BASELINE config)  HuBERT-Soft units, 16 x 20 s of 16 kHz audio
 each with its own value / e2e / roofline / cpu_baseline.
 
 `--impl reference` times the reference's own CPU algorithm on the host cores: the unmodified
@@ -55,7 +56,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=32, help="utterances per GPU per step")
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance (100 fps)")
     ap.add_argument("--precision", type=int, default=3, help="3 bf16x3 tensor-core (parity grade, default), 1 bf16, 0 fp32 CUDA cores")
-    ap.add_argument("--workload", default="svc", choices=["svc", "whisper"],
+    ap.add_argument("--workload", default="svc", choices=["svc", "whisper", "hubert"],
                     help="svc = BASELINE configs[3] (headline); whisper = configs[2] PPG extraction, 16 x 30 s log-mel")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-subconfigs", action="store_true", help="skip the configs[1] / configs[2] sub-records")
@@ -459,7 +460,8 @@ def run_ours(args, hp, sd):
         torch.cuda.empty_cache()
         sub = {}
         for name, fn in (("generator", lambda: bench_generator(args, hp, dev, lib, peaks)),
-                         ("whisper", lambda: bench_whisper(args, dev, lib, peaks))):
+                         ("whisper", lambda: bench_whisper(args, dev, lib, peaks)),
+                         ("hubert", lambda: bench_hubert(args, dev, lib, peaks))):
             try:
                 sub[name] = fn()
             except Exception as e:  # a sub-record must never take the headline down
@@ -639,12 +641,64 @@ def bench_whisper(args, dev, lib, peaks):
     return out
 
 
+def bench_hubert(args, dev, lib, peaks):
+    """SURVEY.md §8f-2 (not a BASELINE config): HuBERT-Soft units, 16 x 20 s chunks of 16 kHz audio per step
+    (hubert/inference.py:30-33 chunk size) -> [16, 1000, 256]."""
+    from whisper_vits_svc_b200 import hubert_infer, synth
+    sd = synth.hubert_checkpoint(1234)
+    model = hubert_infer.HubertSoftB200(sd, dev)
+    B, n = 16, 20 * 16000
+    steps = args.steps
+    g = torch.Generator().manual_seed(0)
+    wav = torch.randn(B, n, generator=g) * 0.1
+    wav_d = wav.to(dev)
+    T = model.frames(n)
+    ms = timed_region(lambda: model.units(wav_d), steps, max(args.warmup, 3), dev) / steps
+    pipe = E2EPipeline(dev, {"wav": wav.pin_memory()}, (B, T, 256), lambda x: model.units(x["wav"]))
+    pipe.run(1)
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); pipe.run(steps); e1.record(); torch.cuda.synchronize(dev)
+    ms_e2e = e0.elapsed_time(e1) / steps
+    lib.svcb_timing_enable(1)
+    for _ in range(steps):
+        model.units(wav_d)
+    torch.cuda.synchronize(dev)
+    rep = lib.svcb_timing_report().decode(); lib.svcb_timing_enable(0)
+    rows, table, tot = kernel_families(rep, steps)
+    audio_s = 20.0 * B
+    # conv stem 2 * 512 * 512 * (3 * (32007 + 16003 + 8001 + 4000) + 2 * (2000 + 1000)) + conv0, pos conv, 12 layers, proj
+    flops_item = (2 * 512 * 512 * (3 * 60011 + 2 * 3000) + 2 * 512 * 10 * 64015 + 2 * T * 768 * 48 * 128
+                  + 2 * T * 512 * 768 + 12 * (2 * T * 768 * (2304 + 768 + 2 * 3072) + 4 * T * T * 768) + 2 * T * 768 * 256)
+    out = {"metric": "audio seconds/sec (HuBERT-Soft units)", "value": audio_s / (ms * 1e-3), "unit": "audio s/s",
+           "ms_per_step": ms, "dtype": "bf16 (tcgen05 GEMMs / attention, fp32 accumulate, fp32 residual stream); conv0 + GroupNorm f32",
+           "config": {"workload": f"SURVEY 8f-2: 16 x 20 s of 16 kHz audio [16, 320000] -> units [16, {T}, 256], 12 layers",
+                      "tflops_model": flops_item * B / (ms * 1e-3) / 1e12},
+           "e2e": {"value": audio_s / (ms_e2e * 1e-3), "unit": "audio s/s", "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": pipe.h2d, "d2h_bytes_per_step": pipe.d2h},
+           "roofline": roofline_of(rows[0], tot, steps, peaks), "kernels": table[:8],
+           "gpu_launches": int(sum(r["launches"] for r in rows))}
+    del model, pipe
+    if not args.no_cpu_baseline:
+        from oracle import hubert_oracle as HO
+        cores = cpu_threads()
+        torch.set_num_threads(cores)
+        HO.units(sd, wav[:1, None, :16000])   # warm-up
+        t0 = time.perf_counter()
+        HO.units(sd, wav[:1, None, :])
+        sec = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 20.0 / sec, "unit": "audio s/s", "cores": cores, "kind": "port",
+                               "sample": f"one 20 s chunk (1 of the 16), oracle port of HubertSoft.units, torch fp32, "
+                                         f"{cores} threads, {sec:.1f} s"}
+    return out
+
+
 def run_whisper(args):
     from whisper_vits_svc_b200 import _lib
     assert torch.cuda.is_available()
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)))
     torch.cuda.set_device(dev)
-    out = bench_whisper(args, dev, _lib.load(), load_peaks())
+    out = (bench_hubert if args.workload == "hubert" else bench_whisper)(args, dev, _lib.load(), load_peaks())
     out.update({"n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "data": "synthetic"})
     print(json.dumps(out), flush=True)
@@ -652,7 +706,7 @@ def run_whisper(args):
 
 def main():
     args = parse()
-    if args.workload == "whisper":
+    if args.workload in ("whisper", "hubert"):
         return run_whisper(args)
     from whisper_vits_svc_b200 import hparams, synth
     hp = hparams.load_hparams(os.path.join(ROOT, "configs", "base.yaml"))

@@ -182,9 +182,11 @@ int32_t svcb_hubert_frames(int32_t n_samples);
 size_t svcb_hubert_workspace_bytes(const svcb_hubert* h, int32_t B, int32_t n_samples);
 /* Replaces HubertSoft.units (hubert/hubert_model.py:68-72): wav [B, n_samples] fp32 (16 kHz, equal-length chunks) ->
  * out [B, svcb_hubert_frames(n_samples), 256] fp32.  taps: null, or 5 device pointers (each may be null) that receive
- * the time-major intermediates [B*T, 512 | 768]: 0 features, 1 projected, 2 embedded, 3 after layer 0, 4 encoded. */
+ * the time-major intermediates [B*T, 512 | 768]: 0 features, 1 projected, 2 embedded, 3 after layer 0, 4 encoded.
+ * flags: bit 0 = the six stride-2 convs of the stem in fp32 on the CUDA cores instead of bf16 tcgen05 GEMMs,
+ * bit 1 = the grouped positional convolution likewise. */
 int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_t B, int32_t n_samples, void* ws,
-                      size_t ws_bytes, float* const* taps, svcb_stream stream);
+                      size_t ws_bytes, float* const* taps, int32_t flags, svcb_stream stream);
 
 /* Replaces whisper.audio.log_mel_spectrogram (whisper/audio.py:68-100) plus the extractor's mel noise
  * (whisper/inference.py:46,58) for B equal-length chunks of 16 kHz audio already on the device:

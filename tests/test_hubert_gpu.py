@@ -53,15 +53,19 @@ def test_units_stages_vs_oracle(models):
     from oracle import hubert_oracle as ho, make_golden as mg
     sd, model = models(31)
     wav = mg.hubert_wav(77, 2, 48000)
-    taps_o, taps = {}, {}
+    taps_o, taps, taps32 = {}, {}, {}
     ref = ho.units(sd, wav, taps_o)
     got = model.units(wav, taps).cpu()
     T = ho.frames(48000)
     assert got.shape == ref.shape == (2, T, 256) and model.frames(48000) == T
-    feats = taps["features"].cpu()                                    # time-major here, channel-major in the oracle
-    e = max_abs(feats, taps_o["features"].transpose(1, 2))
-    print(f"features max-abs {e:.3e} (rms {taps_o['features'].pow(2).mean().sqrt():.3f})")
+    feats_o = taps_o["features"].transpose(1, 2)                      # time-major here, channel-major in the oracle
+    got32 = model.units(wav, taps32, fp32_stem=True).cpu()            # flags bit 0: the stride-2 convs in fp32
+    e = max_abs(taps32["features"].cpu(), feats_o)
+    print(f"features (fp32 stem) max-abs {e:.3e} (rms {feats_o.pow(2).mean().sqrt():.3f})")
     assert e <= 2e-4
+    r = rel_l2(taps["features"].cpu(), feats_o)
+    print(f"features (tcgen05 stem, bf16) rel-l2 {r:.3e}; units fp32-stem vs tcgen05-stem rel-l2 {rel_l2(got, got32):.3e}")
+    assert r <= 1e-2 and rel_l2(got32, ref) <= 2e-2
     for nm in ("projected", "embedded", "layer0", "encoded"):
         r = rel_l2(taps[nm].cpu(), taps_o[nm])
         print(f"{nm}: rel-l2 {r:.3e}")

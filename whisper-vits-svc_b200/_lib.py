@@ -83,7 +83,7 @@ SIGNATURES = {
     "svcb_hubert_destroy": (None, [c_void_p]),
     "svcb_hubert_frames": (c_int32, [c_int32]),
     "svcb_hubert_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
-    "svcb_hubert_units": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "svcb_hubert_units": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_size_t, c_void_p, c_int32, c_void_p]),
     "svcb_whisper_log_mel": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "svcb_op_gemm_bf16_scratch_bytes": (c_size_t, [c_int32] * 3),
     "svcb_op_gemm_bf16": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p, c_size_t, c_void_p]),

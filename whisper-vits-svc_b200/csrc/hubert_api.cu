@@ -7,10 +7,16 @@
 //   nn.TransformerEncoderLayer(768, 12, 3072, gelu, post-LN) (:131-153) -> Linear(768,256).
 // The transformer runs on the PPG extractor's kernels: tcgen05 GEMMs over bf16 tile images (whisper_gemm.cu), the
 // tcgen05 attention with P in tensor memory (whisper_attn_tc.cu: 12 heads of 64, scores / 8), `ln_rows` writing the
-// normalised rows both as the next GEMM's A image and as the fp32 residual stream (post-LN).  The convolutional stem
-// runs in fp32 on the CUDA cores (`conv1d`; 97 GFLOP per 20 s chunk — the tensor-core im2col form of the Whisper stem
-// is the next step), the last conv writing time-major rows through its output strides; GroupNorm is one CTA per
-// (item, channel) row.
+// normalised rows both as the next GEMM's A image and as the fp32 residual stream (post-LN).
+// Convolutional stem (97 GFLOP per 20 s chunk): conv0 (one input channel) and GroupNorm (one CTA per (item, channel)
+// row) in fp32 on the CUDA cores; the six stride-2 convs as tcgen05 GEMMs over im2col tile images — the first image is
+// built from the normalised conv0 output, every GEMM's epilogue (6) applies GELU and scatters straight into the NEXT
+// conv's image, the last one writes the fp32 time-major rows LayerNorm reads.  flags bit 0 selects the all-fp32 stem
+// (`conv1d`, the last conv writing time-major rows through its output strides) for parity work.
+// Positional conv (Conv1d(768, 768, 128, groups 16): 9.4 GFLOP per 1000 frames): per group an im2col tile image
+// (K = 128 taps x 48 channels) times a [256 (48 used), K] weight image, epilogue 7 = GELU + residual into the group's 48
+// columns of the 768-wide rows; flags bit 1 selects the fp32 CUDA-core form (32 `conv1d` launches, 16 ms per 16 x 20 s).
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <string>
@@ -20,7 +26,9 @@
 
 namespace svcb {
 int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
-                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0);
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0, int aux = 0);
+int launch_im2col_rows_image(const float* x, void* img, int B, int T, int ld, int c0, int cg, int taps, int pad, cudaStream_t s);
+int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s, int taps = 3, int pad = 1);
 int launch_whisper_attention_tc(const void* qkv_img, void* out_img, int B, int T, int D, int heads, int vswap, cudaStream_t s);
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, void* y, int M, int D, bool out_bf16,
                    cudaStream_t s, float* y32 = nullptr);
@@ -68,7 +76,7 @@ static size_t align256h(size_t x) { return (x + 255) & ~(size_t)255; }
 struct HLayout {
   int T[7];            // frames after conv0 .. conv6
   int M;
-  size_t bufa, bufb, rows, a512, x, y, a, qkv, att, mid, total;
+  size_t bufa, bufb, imgb, posimg, rows, a512, x, y, a, qkv, att, mid, total;   // bufb doubles as the first im2col image
 };
 static HLayout hubert_layout(int B, int n_samples) {
   HLayout L;
@@ -79,7 +87,12 @@ static HLayout hubert_layout(int B, int n_samples) {
   const size_t Mp = ((size_t)L.M + 127) / 128 * 128;
   size_t off = 0;
   L.bufa = off; off = align256h(off + (size_t)B * HB_C * L.T[0] * 4);
-  L.bufb = off; off = align256h(off + (size_t)B * HB_C * (L.T[1] > 0 ? L.T[1] : 1) * 4);
+  {  // fp32 stem: ping-pong activations [B, 512, T1]; tensor-core stem: im2col images [ceil(B T_i / 128) * 128][taps * 512] bf16
+    const size_t m1 = ((size_t)B * (L.T[1] > 0 ? L.T[1] : 1) + 127) / 128 * 128, m2 = ((size_t)B * (L.T[2] > 0 ? L.T[2] : 1) + 127) / 128 * 128;
+    L.bufb = off; off = align256h(off + std::max((size_t)B * HB_C * (L.T[1] > 0 ? L.T[1] : 1) * 4, m1 * 3 * HB_C * 2));
+    L.imgb = off; off = align256h(off + m2 * 3 * HB_C * 2);
+  }
+  L.posimg = off; off = align256h(off + Mp * (size_t)HB_PK * (HB_D / HB_PG) * 2);   // one group's im2col image, K = 128 * 48
   L.rows = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_C * 4);
   L.a512 = off; off = align256h(off + Mp * HB_C * 2);
   L.x = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_D * 4);
@@ -99,7 +112,7 @@ using namespace svcb;
 struct svcb_hubert {
   int n_layer = 0;
   std::map<std::string, std::pair<const float*, uint64_t>> tensors;
-  const float *conv0_w, *gn_g, *gn_b, *conv_w[6], *fp_lng, *fp_lnb, *fp_w, *fp_b, *pos_w[HB_PG][2], *pos_b, *norm_g, *norm_b,
+  const float *conv0_w, *gn_g, *gn_b, *conv_w[6], *conv_wimg[6], *fp_lng, *fp_lnb, *fp_w, *fp_b, *pos_w[HB_PG][2], *pos_b, *pos_wimg[HB_PG], *pos_bimg[HB_PG], *norm_g, *norm_b,
       *proj_w, *proj_b;
   std::vector<HLayer> layers;
 };
@@ -137,12 +150,19 @@ int svcb_hubert_create(const void* dev_blob, size_t blob_bytes, const svcb_tenso
   const uint64_t C = HB_C, D = HB_D, FF = HB_FF;
   h->conv0_w = get("fe.conv0.w", 10 * C);
   h->gn_g = get("fe.gn.g", C); h->gn_b = get("fe.gn.b", C);
-  for (int i = 0; i < 6; ++i) h->conv_w[i] = get("fe.conv" + std::to_string(i + 1) + ".w", C * kHbKernels[i] * C);
+  for (int i = 0; i < 6; ++i) {
+    h->conv_w[i] = get("fe.conv" + std::to_string(i + 1) + ".w", C * kHbKernels[i] * C);
+    h->conv_wimg[i] = get("fe.conv" + std::to_string(i + 1) + ".wimg", C * kHbKernels[i] * C / 2);
+  }
   h->fp_lng = get("fp.ln.g", C); h->fp_lnb = get("fp.ln.b", C);
   h->fp_w = get("fp.w", D * C / 2); h->fp_b = get("fp.b", D);
   for (int g = 0; g < HB_PG; ++g)
     for (int hf = 0; hf < 2; ++hf)
       h->pos_w[g][hf] = get("pos." + std::to_string(g) + "." + std::to_string(hf) + ".w", (uint64_t)(D / HB_PG) * HB_PK * HB_PHALF);
+  for (int g = 0; g < HB_PG; ++g) {
+    h->pos_wimg[g] = get("pos." + std::to_string(g) + ".wimg", (uint64_t)256 * HB_PK * (D / HB_PG) / 2);
+    h->pos_bimg[g] = get("pos." + std::to_string(g) + ".bimg", 256);
+  }
   h->pos_b = get("pos.b", D);
   h->norm_g = get("norm.g", D); h->norm_b = get("norm.b", D);
   h->layers.resize(n_layer);
@@ -172,7 +192,7 @@ size_t svcb_hubert_workspace_bytes(const svcb_hubert* h, int32_t B, int32_t n_sa
 }
 
 int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_t B, int32_t n_samples, void* ws,
-                      size_t ws_bytes, float* const* taps, svcb_stream stream) {
+                      size_t ws_bytes, float* const* taps, int32_t flags, svcb_stream stream) {
   if (!h || !wav || !out || B <= 0 || n_samples <= 0) { set_error("svcb_hubert_units: bad argument"); return SVCB_E_BAD_SHAPE; }
   const HLayout L = hubert_layout(B, n_samples);
   const int T = L.T[6], M = L.M;
@@ -203,8 +223,20 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
     groupnorm_gelu_rows_kernel<<<B * HB_C, 256, 0, s>>>(bufa, h->gn_g, h->gn_b, HB_C, L.T[0], 1e-5f);
     SVCB_LAUNCH_CHECK("groupnorm_gelu_rows");
   }
+  if (!(flags & 1)) {
+    // conv1 .. conv6 + GELU on the tensor cores: A_i[b * T_i + t][j * 512 + ci] = h_{i-1}[b][ci][2 t + j]
+    void* img[2] = {base + L.bufb, base + L.imgb};
+    SVCB_TRY(launch_im2col_s2_image(bufa, img[0], B, HB_C, L.T[0], L.T[1], s, kHbKernels[0], 0));
+    for (int i = 1; i <= 6; ++i) {
+      const int K = kHbKernels[i - 1] * HB_C, Mi = B * L.T[i];
+      if (i < 6)   // GELU, scattered into conv_{i+1}'s image
+        SVCB_TRY(launch_gemm_tc(img[(i - 1) & 1], h->conv_wimg[i - 1], nullptr, img[i & 1], nullptr, Mi, HB_C, K, 6, s, L.T[i], kHbKernels[i]));
+      else         // GELU -> fp32 rows [B * T, 512]
+        SVCB_TRY(launch_gemm_tc(img[(i - 1) & 1], h->conv_wimg[i - 1], nullptr, rows, nullptr, Mi, HB_C, K, 3, s));
+    }
+  }
   const float* cur = bufa;
-  for (int i = 1; i <= 6; ++i) {   // conv1 .. conv6 + GELU; the last one writes time-major rows [B * T, 512]
+  for (int i = 1; i <= 6 && (flags & 1); ++i) {   // fp32 stem: conv1 .. conv6 + GELU; the last one writes time-major rows
     float* dst = i == 6 ? rows : (cur == bufa ? bufb : bufa);
     ConvParams p;
     p.x = cur; p.sxb = (long long)HB_C * L.T[i - 1]; p.sxc = L.T[i - 1]; p.sxt = 1;
@@ -223,7 +255,12 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
   SVCB_TRY(launch_gemm_tc(a512, h->fp_w, h->fp_b, x, nullptr, M, HB_D, HB_C, 2, s));
   SVCB_TRY(tap(1, x, (size_t)M * HB_D));
   // y = x + GELU(pos_conv(x)[..., :-1]): 16 groups of 48 channels, 128 taps, two 24-channel halves per group
-  for (int g = 0; g < HB_PG; ++g)
+  for (int g = 0; g < HB_PG && !(flags & 2); ++g) {   // tensor cores: per group an im2col image (K = 128 x 48) x [256 (48 used), K]
+    const int cg = HB_D / HB_PG, c0 = g * cg;
+    SVCB_TRY(launch_im2col_rows_image(x, base + L.posimg, B, T, HB_D, c0, cg, HB_PK, HB_PK / 2, s));
+    SVCB_TRY(launch_gemm_tc(base + L.posimg, h->pos_wimg[g], h->pos_bimg[g], y + c0, x + c0, M, 256, HB_PK * cg, 7, s, cg, HB_D));
+  }
+  for (int g = 0; g < HB_PG && (flags & 2); ++g)       // flags bit 1: fp32 on the CUDA cores
     for (int hf = 0; hf < 2; ++hf) {
       const int ci0 = g * (HB_D / HB_PG), co0 = ci0 + hf * HB_PHALF;
       ConvParams p;

@@ -12,9 +12,9 @@
 
 namespace svcb {
 int launch_gemm_tc(const void* A_bf16, const void* W_bf16, const float* bias, void* out, const float* res,
-                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0);
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod = 0, int aux = 0);
 int launch_im2col_s1_image(const float* mel, void* img, int B, int n_mels, int n, cudaStream_t s);
-int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s);
+int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s, int taps = 3, int pad = 1);
 int launch_whisper_attention(const void* qkv_bf16, void* out_bf16, int B, int T, int D, int heads, int img,
                              cudaStream_t s);
 int launch_rowmajor_to_image(const void* src, void* dst, int R, int K, int rows, cudaStream_t s);

@@ -30,8 +30,13 @@ namespace svcb {
 // 5: the stem's conv1 (rows = items x res_mod frames): GELU(acc + bias) scattered straight into conv2's im2col tile
 //    image A2[b * n2 + t2][j * N + co] = h1[b][co][2 t2 + j - 1] (frame t feeds (t/2, j=1) when even, ((t+1)/2, j=0)
 //    and ((t-1)/2, j=2) when odd) — no h1 tensor, no im2col pass; the caller zeroes the image once (t = -1 taps, pad rows)
+// 6: a stride-2 VALID convolution of the HuBERT stem feeding the next one (rows = items x res_mod frames, aux = taps of
+//    the NEXT conv, 2 or 3): GELU(acc + bias) scattered into the next conv's im2col tile image
+//    A[b * Tn + t2][j * N + co] = h[b][co][2 t2 + j], Tn = (res_mod - aux) / 2 + 1 (every entry of the image is written)
+// 7: fp32 out[m * aux + col] = GELU(acc + bias) + res[m * aux + col] for the first res_mod columns only (aux = leading
+//    dimension of out / res): one group of HuBERT's grouped positional convolution, N padded from 48 to 256
 enum GemmEpi : int { EPI_BF16_ROWMAJOR = 0, EPI_GELU_BF16_IMAGE = 1, EPI_RESID_F32 = 2, EPI_GELU_ADD_F32 = 3, EPI_QKV_HEADS = 4,
-                     EPI_GELU_CONV2_IMG = 5 };
+                     EPI_GELU_CONV2_IMG = 5, EPI_GELU_VALID_S2_IMG = 6, EPI_GELU_ADD_F32_LD = 7 };
 
 constexpr int GM_BM = 128, GM_BK = 64, GM_STAGES = 4;
 
@@ -43,7 +48,7 @@ __host__ __device__ inline size_t img_off(int m, int k, int KT) {
 template <int BN, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __restrict__ Wimg,
-               const float* __restrict__ bias, void* out, const float* res, int M, int N, int K, int res_mod) {
+               const float* __restrict__ bias, void* out, const float* res, int M, int N, int K, int res_mod, int aux) {
   constexpr uint32_t A_BYTES = GM_BM * GM_BK * 2, B_BYTES = BN * GM_BK * 2, ST_BYTES = A_BYTES + B_BYTES;
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[GM_STAGES], bar_empty[GM_STAGES], t_full[2], t_empty[2];
@@ -136,11 +141,19 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
           float f[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (bias ? __ldg(bias + n0 + c0 + j) : 0.f);
-          if (EPI == EPI_GELU_ADD_F32 || EPI == EPI_GELU_CONV2_IMG) {
+          if (EPI == EPI_GELU_ADD_F32 || EPI == EPI_GELU_CONV2_IMG || EPI == EPI_GELU_VALID_S2_IMG || EPI == EPI_GELU_ADD_F32_LD) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = 0.5f * f[j] * (1.f + erff(f[j] * 0.70710678118654752440f));
           }
-          if (EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) {
+          if (EPI == EPI_GELU_ADD_F32_LD) {
+            float* o = static_cast<float*>(out) + (size_t)m * aux;
+            const float* rr = res + (size_t)m * aux;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int col = n0 + c0 + j;
+              if (col < res_mod) o[col] = f[j] + rr[col];
+            }
+          } else if (EPI == EPI_RESID_F32 || EPI == EPI_GELU_ADD_F32) {
             float* o = static_cast<float*>(out) + (size_t)m * N + n0 + c0;
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
@@ -153,7 +166,20 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
               if (EPI == EPI_GELU_BF16_IMAGE) x = 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
               h[j] = __float2bfloat16_rn(x);
             }
-            if (EPI == EPI_GELU_CONV2_IMG) {
+            if (EPI == EPI_GELU_VALID_S2_IMG) {
+              __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
+              const int nfr = res_mod, Tn = (nfr - aux) / 2 + 1, KT2 = aux * N / GM_BK;
+              const int bi = m / nfr, t = m - bi * nfr;
+              const uint4 q0 = *reinterpret_cast<const uint4*>(h), q1 = *reinterpret_cast<const uint4*>(h + 8);
+              auto put = [&](int t2, int j) {   // frame t is tap j of output frame t2: t = 2 t2 + j
+                if (t2 >= 0 && t2 < Tn) {
+                  *reinterpret_cast<uint4*>(ob + img_off(bi * Tn + t2, j * N + n0 + c0, KT2)) = q0;
+                  *reinterpret_cast<uint4*>(ob + img_off(bi * Tn + t2, j * N + n0 + c0 + 8, KT2)) = q1;
+                }
+              };
+              if (t & 1) put((t - 1) >> 1, 1);
+              else { put(t >> 1, 0); if (aux == 3) put((t >> 1) - 1, 2); }
+            } else if (EPI == EPI_GELU_CONV2_IMG) {
               __nv_bfloat16* ob = static_cast<__nv_bfloat16*>(out);
               const int nfr = res_mod, n2 = (nfr - 1) / 2 + 1, KT2 = 3 * N / GM_BK;
               const int bi = m / nfr, t = m - bi * nfr;
@@ -201,7 +227,7 @@ gemm_tc_kernel(const __nv_bfloat16* __restrict__ Aimg, const __nv_bfloat16* __re
 
 template <int BN, int EPI>
 static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const float* bias, void* out,
-                         const float* res, int M, int N, int K, int res_mod, cudaStream_t s) {
+                         const float* res, int M, int N, int K, int res_mod, cudaStream_t s, int aux = 0) {
   constexpr size_t smem = (size_t)GM_STAGES * (GM_BM * GM_BK * 2 + BN * GM_BK * 2);
   static DevSmemCache attr_cache;
   SVCB_CUDA_CHECK(ensure_dyn_smem(gemm_tc_kernel<BN, EPI>, smem, attr_cache));
@@ -211,14 +237,14 @@ static int launch_gemm_t(const __nv_bfloat16* A, const __nv_bfloat16* W, const f
   const int grid = std::min(ntiles, n_sm);
   KernelScope ks("whisper_gemm_tc", s, 2.0 * M * (double)N * K,
                  2.0 * ((double)M * K + (double)N * K) + (EPI == EPI_RESID_F32 ? 8.0 : EPI == EPI_GELU_ADD_F32 ? 4.0 : 2.0) * M * (double)N);
-  gemm_tc_kernel<BN, EPI><<<grid, 320, smem, s>>>(A, W, bias, out, res, M, N, K, res_mod);
+  gemm_tc_kernel<BN, EPI><<<grid, 320, smem, s>>>(A, W, bias, out, res, M, N, K, res_mod, aux);
   SVCB_LAUNCH_CHECK("gemm_tc");
   return SVCB_OK;
 }
 
 // A_img: tile image [ceil(M/128)][K/64][8][128][8]; W_img: tile image [N/256][K/64][8][256][8]
 int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void* out, const float* res,
-                   int M, int N, int K, int epi, cudaStream_t s, int res_mod) {
+                   int M, int N, int K, int epi, cudaStream_t s, int res_mod, int aux) {
   if (M <= 0) return SVCB_OK;
   if (K % 64 || N % 256) { set_error("gemm_tc: need K % 64 == 0 and N % 256 == 0"); return SVCB_E_BAD_SHAPE; }
   const __nv_bfloat16* A = static_cast<const __nv_bfloat16*>(A_img);
@@ -230,11 +256,19 @@ int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void
     case EPI_GELU_CONV2_IMG:
       if (res_mod <= 0 || M % res_mod || N % GM_BK) { set_error("gemm_tc: epilogue 5 needs rows = items x res_mod frames"); return SVCB_E_BAD_SHAPE; }
       return launch_gemm_t<256, EPI_GELU_CONV2_IMG>(A, W, bias, out, res, M, N, K, res_mod, s);
+    case EPI_GELU_ADD_F32_LD:
+      if (!res || res_mod <= 0 || res_mod > N || aux < res_mod) { set_error("gemm_tc: epilogue 7 needs res, valid columns (res_mod) and a leading dimension (aux)"); return SVCB_E_BAD_SHAPE; }
+      return launch_gemm_t<256, EPI_GELU_ADD_F32_LD>(A, W, bias, out, res, M, N, K, res_mod, s, aux);
+    case EPI_GELU_VALID_S2_IMG:
+      if (res_mod <= 0 || M % res_mod || N % GM_BK || (aux != 2 && aux != 3) || res_mod < aux) {
+        set_error("gemm_tc: epilogue 6 needs rows = items x res_mod frames and aux = 2 or 3 taps");
+        return SVCB_E_BAD_SHAPE;
+      }
+      return launch_gemm_t<256, EPI_GELU_VALID_S2_IMG>(A, W, bias, out, res, M, N, K, res_mod, s, aux);
     case EPI_QKV_HEADS:
       if (res_mod <= 0 || M % res_mod || N % 192) { set_error("gemm_tc: epilogue 4 needs rows = items x res_mod, N = 3 x heads x 64"); return SVCB_E_BAD_SHAPE; }
       return launch_gemm_t<256, EPI_QKV_HEADS>(A, W, bias, out, res, M, N, K, res_mod, s);
     case EPI_GELU_ADD_F32:
-      if (!res) { set_error("gemm_tc: epilogue 3 needs the addend"); return SVCB_E_BAD_SHAPE; }
       return launch_gemm_t<256, EPI_GELU_ADD_F32>(A, W, bias, out, res, M, N, K, res_mod, s);
   }
   set_error("gemm_tc: unknown epilogue");
@@ -246,7 +280,8 @@ int launch_gemm_tc(const void* A_img, const void* W_img, const float* bias, void
 // (zero outside the sequence and in the rows that pad M to whole 128-row tiles), bf16.
 // One CTA = one (row tile, k tile): a k tile of 64 lies inside one tap j because D % 64 == 0.
 __global__ void __launch_bounds__(256)
-im2col_s2_image_kernel(const float* __restrict__ h1, __nv_bfloat16* __restrict__ img, int D, int n, int n2, int M) {
+im2col_s2_image_kernel(const float* __restrict__ h1, __nv_bfloat16* __restrict__ img, int D, int n, int n2, int M, int taps,
+                       int pad) {
   __shared__ float tile[64][129];
   const int mt = blockIdx.x, kt = blockIdx.y, tid = threadIdx.x;
   const int j = (kt * 64) / D, ci0 = (kt * 64) % D;
@@ -256,13 +291,13 @@ im2col_s2_image_kernel(const float* __restrict__ h1, __nv_bfloat16* __restrict__
     float v = 0.f;
     if (m < M) {
       const int b = m / n2, t2 = m - b * n2;
-      const int t = 2 * t2 + j - 1;
+      const int t = 2 * t2 + j - pad;
       if (t >= 0 && t < n) v = __ldg(h1 + ((size_t)b * D + ci0 + cc) * n + t);
     }
     tile[cc][r] = v;
   }
   __syncthreads();
-  const int KT = 3 * D / 64;
+  const int KT = taps * D / 64;
   __nv_bfloat16* dst = img + ((size_t)mt * KT + kt) * (GM_BM * GM_BK);
   for (int idx = tid; idx < 8 * 128; idx += 256) {
     const int kc = idx >> 7, r = idx & 127;
@@ -312,12 +347,51 @@ int launch_im2col_s1_image(const float* mel, void* img, int B, int n_mels, int n
   return SVCB_OK;
 }
 
-int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s) {
+// HuBERT's positional convolution (Conv1d(768, 768, 128, padding 64, groups 16), hubert_model.py:115-121), one group:
+// A[m = b*T + t][k = j*cg + ci] = x[b*T + t + j - pad][c0 + ci] from the fp32 time-major rows x [B*T, ld] (zero outside
+// the item), cg = 48 channels per group = 6 octets per tap, K = taps * cg.  One CTA = one (row tile, k tile).
+__global__ void __launch_bounds__(256)
+im2col_rows_image_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ img, int T, int M, int ld, int c0, int cg,
+                         int pad, int KT) {
+  const int mt = blockIdx.x, kt = blockIdx.y, opt = cg / 8;   // octets per tap
+  __nv_bfloat16* dst = img + ((size_t)mt * KT + kt) * (GM_BM * GM_BK);
+  for (int idx = threadIdx.x; idx < 8 * 128; idx += 256) {
+    const int kc = idx >> 7, r = idx & 127;
+    const int m = mt * 128 + r, o = kt * 8 + kc;   // global octet index along K
+    const int j = o / opt, ci = (o - j * opt) * 8;
+    __align__(16) __nv_bfloat16 h[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) h[e] = __float2bfloat16_rn(0.f);
+    if (m < M) {
+      const int b = m / T, t = m - b * T + j - pad;
+      if (t >= 0 && t < T) {
+        const float4* s4 = reinterpret_cast<const float4*>(x + ((size_t)b * T + t) * ld + c0 + ci);
+        const float4 u0 = __ldg(s4), u1 = __ldg(s4 + 1);
+        h[0] = __float2bfloat16_rn(u0.x); h[1] = __float2bfloat16_rn(u0.y); h[2] = __float2bfloat16_rn(u0.z); h[3] = __float2bfloat16_rn(u0.w);
+        h[4] = __float2bfloat16_rn(u1.x); h[5] = __float2bfloat16_rn(u1.y); h[6] = __float2bfloat16_rn(u1.z); h[7] = __float2bfloat16_rn(u1.w);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)(kc * 128 + r) * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+int launch_im2col_rows_image(const float* x, void* img, int B, int T, int ld, int c0, int cg, int taps, int pad, cudaStream_t s) {
+  if (cg % 8 || (taps * cg) % 64 || (c0 % 4) || (ld % 4)) { set_error("im2col_rows_image: channel group must be octets, K a multiple of 64"); return SVCB_E_BAD_SHAPE; }
+  const int M = B * T, KT = taps * cg / 64;
+  dim3 grid((M + 127) / 128, KT);
+  KernelScope ks("im2col_rows_image", s, 0.0, (double)M * taps * cg * 2 + 4.0 * M * cg);
+  im2col_rows_image_kernel<<<grid, 256, 0, s>>>(x, static_cast<__nv_bfloat16*>(img), T, M, ld, c0, cg, pad, KT);
+  SVCB_LAUNCH_CHECK("im2col_rows_image");
+  return SVCB_OK;
+}
+
+// taps / pad: 3 / 1 for Whisper's conv2; 3 / 0 for the first stride-2 conv of the HuBERT stem (valid convolution)
+int launch_im2col_s2_image(const float* h1, void* img, int B, int D, int n, int n2, cudaStream_t s, int taps, int pad) {
   if (D % 64) { set_error("im2col_s2_image: D must be a multiple of 64"); return SVCB_E_BAD_SHAPE; }
   const int M = B * n2;
-  dim3 grid((M + 127) / 128, 3 * D / 64);
-  KernelScope ks("im2col_s2_image", s, 0.0, (double)M * 3 * D * 2 + 4.0 * B * D * (double)n);
-  im2col_s2_image_kernel<<<grid, 256, 0, s>>>(h1, static_cast<__nv_bfloat16*>(img), D, n, n2, M);
+  dim3 grid((M + 127) / 128, taps * D / 64);
+  KernelScope ks("im2col_s2_image", s, 0.0, (double)M * taps * D * 2 + 4.0 * B * D * (double)n);
+  im2col_s2_image_kernel<<<grid, 256, 0, s>>>(h1, static_cast<__nv_bfloat16*>(img), D, n, n2, M, taps, pad);
   SVCB_LAUNCH_CHECK("im2col_s2_image");
   return SVCB_OK;
 }

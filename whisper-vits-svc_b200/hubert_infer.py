@@ -33,7 +33,10 @@ def pack_hubert(sd: Dict[str, torch.Tensor]) -> Tuple[List[Tuple[str, torch.Tens
     put("fe.conv0.w", pack.pack_conv(sd[fe + "conv0.weight"].float()))
     put("fe.gn.g", sd[fe + "norm0.weight"]); put("fe.gn.b", sd[fe + "norm0.bias"])
     for i in range(1, 7):
-        put(f"fe.conv{i}.w", pack.pack_conv(sd[fe + f"conv{i}.weight"].float()))
+        wi = sd[fe + f"conv{i}.weight"].float()                                 # [512, 512, k]
+        put(f"fe.conv{i}.w", pack.pack_conv(wi))                                # fp32 stem (flags bit 0)
+        # tensor-core stem: W[co][j * 512 + ci] as a bf16 tile image (csrc/whisper_gemm.cu)
+        items.append((f"fe.conv{i}.wimg", _bf16_as_f32(wi.permute(0, 2, 1).reshape(wi.shape[0], -1))))
     put("fp.ln.g", sd["feature_projection.norm.weight"]); put("fp.ln.b", sd["feature_projection.norm.bias"])
     items.append(("fp.w", _bf16_as_f32(sd["feature_projection.projection.weight"])))
     put("fp.b", sd["feature_projection.projection.bias"])
@@ -45,6 +48,14 @@ def pack_hubert(sd: Dict[str, torch.Tensor]) -> Tuple[List[Tuple[str, torch.Tens
         for h in range(per_g // POS_HALF):
             rows = slice(g * per_g + h * POS_HALF, g * per_g + (h + 1) * POS_HALF)
             put(f"pos.{g}.{h}.w", pack.pack_conv(w[rows]))
+    for g in range(POS_GROUPS):   # tensor-core form: W_g[co][j * 48 + ci], output channels padded from 48 to 256
+        wg = w[g * per_g:(g + 1) * per_g]                                       # [48, 48, 128]
+        wp = torch.zeros(256, wg.shape[1] * wg.shape[2])
+        wp[:per_g] = wg.permute(0, 2, 1).reshape(per_g, -1)
+        items.append((f"pos.{g}.wimg", _bf16_as_f32(wp)))
+        bp = torch.zeros(256)
+        bp[:per_g] = sd[pc + "bias"].float()[g * per_g:(g + 1) * per_g]
+        put(f"pos.{g}.bimg", bp)
     put("pos.b", sd[pc + "bias"])
     put("norm.g", sd["norm.weight"]); put("norm.b", sd["norm.bias"])
     L = n_layers(sd)
@@ -104,7 +115,8 @@ class HubertSoftB200:
         return int(_lib.load().svcb_hubert_frames(int(n_samples)))
 
     @torch.no_grad()
-    def units(self, wav: torch.Tensor, taps: dict | None = None) -> torch.Tensor:
+    def units(self, wav: torch.Tensor, taps: dict | None = None, fp32_stem: bool = False) -> torch.Tensor:
+        """fp32_stem: the stride-2 convs and the positional conv in fp32 on the CUDA cores (flags 3; parity work)."""
         if wav.dim() == 3:
             wav = wav[:, 0]
         wav = wav.to(self.device, torch.float32).contiguous()
@@ -123,7 +135,7 @@ class HubertSoftB200:
             tap_arr = (ctypes.c_void_p * len(bufs))(*[b.data_ptr() for b in bufs])
         with torch.cuda.device(self.device):
             st = lib.svcb_hubert_units(self._handle, wav.data_ptr(), out.data_ptr(), B, N, self._ws.data_ptr(), self._ws.numel(),
-                                       tap_arr, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                       tap_arr, 3 if fp32_stem else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
         _lib.check(st, "svcb_hubert_units")
         if taps is not None:
             for n, b in zip(TAP_NAMES, bufs):
