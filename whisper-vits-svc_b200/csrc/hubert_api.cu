@@ -8,14 +8,16 @@
 // The transformer runs on the PPG extractor's kernels: tcgen05 GEMMs over bf16 tile images (whisper_gemm.cu), the
 // tcgen05 attention with P in tensor memory (whisper_attn_tc.cu: 12 heads of 64, scores / 8), `ln_rows` writing the
 // normalised rows both as the next GEMM's A image and as the fp32 residual stream (post-LN).
-// Convolutional stem (97 GFLOP per 20 s chunk): conv0 (one input channel) and GroupNorm (one CTA per (item, channel)
-// row) in fp32 on the CUDA cores; the six stride-2 convs as tcgen05 GEMMs over im2col tile images — the first image is
-// built from the normalised conv0 output, every GEMM's epilogue (6) applies GELU and scatters straight into the NEXT
+// Convolutional stem (97 GFLOP per 20 s chunk): conv0 (one input channel, 10 taps) + GroupNorm + GELU in fp32 as two
+// passes over the audio (statistics, then normalise-and-pack) that write conv1's im2col tile image directly; the six
+// stride-2 convs as tcgen05 GEMMs over such images — every GEMM's epilogue (6) applies GELU and scatters straight into the NEXT
 // conv's image, the last one writes the fp32 time-major rows LayerNorm reads.  flags bit 0 selects the all-fp32 stem
 // (`conv1d`, the last conv writing time-major rows through its output strides) for parity work.
 // Positional conv (Conv1d(768, 768, 128, groups 16): 9.4 GFLOP per 1000 frames): per group an im2col tile image
 // (K = 128 taps x 48 channels) times a [256 (48 used), K] weight image, epilogue 7 = GELU + residual into the group's 48
 // columns of the 768-wide rows; flags bit 1 selects the fp32 CUDA-core form (32 `conv1d` launches, 16 ms per 16 x 20 s).
+#include <cuda_bf16.h>
+
 #include <algorithm>
 #include <cstdint>
 #include <map>
@@ -71,12 +73,95 @@ groupnorm_gelu_rows_kernel(float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
+// ---- conv0 + GroupNorm + GELU + the first im2col image in two passes over the AUDIO instead of three over the 2.1 GB
+// conv0 output (conv1d 3.3 + GroupNorm 1.5 + im2col 2.5 ms per 16 x 20 s): conv0 has one input channel and 10 taps, so
+// recomputing it costs less than storing it.
+// pass 1: mean / rstd of every (item, channel) row of y[b, c, t] = sum_j w[c][j] wav[b][5 t + j - 40]
+__global__ void __launch_bounds__(256)
+hubert_conv0_stats_kernel(const float* __restrict__ wav, const float* __restrict__ w0, float2* __restrict__ stats, int N,
+                          int T0, float eps) {
+  __shared__ double red[2][8];
+  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* xb = wav + (size_t)b * N;
+  float w[10];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) w[j] = __ldg(w0 + j * HB_C + c);   // packed [1][10][512]
+  double s = 0.0, q = 0.0;
+  for (int t = tid; t < T0; t += 256) {
+    const int i0 = 5 * t - 40;
+    float y = 0.f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) {
+      const int i = i0 + j;
+      if (i >= 0 && i < N) y = fmaf(w[j], __ldg(xb + i), y);
+    }
+    s += y; q += (double)y * y;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
+  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  __syncthreads();
+  if (tid == 0) {
+    double S = 0.0, Q = 0.0;
+    for (int i = 0; i < 8; ++i) { S += red[0][i]; Q += red[1][i]; }
+    const double mean = S / T0, var = Q / T0 - mean * mean;
+    stats[(size_t)b * HB_C + c] = make_float2((float)mean, (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps)));
+  }
+}
+
+// pass 2: thread = (item, frame t, octet of channels): conv0 again, GroupNorm + GELU, and the bf16 octet stored where
+// conv1's im2col image wants frame t: A1[b * T1 + t2][j * 512 + c] = h0[b][c][2 t2 + j]  (tile image of whisper_gemm.cu)
+__global__ void __launch_bounds__(128)
+hubert_conv0_pack_kernel(const float* __restrict__ wav, const float* __restrict__ w0, const float2* __restrict__ stats,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ img,
+                         int N, int T0, int T1) {
+  __shared__ float ws[10][8];
+  __shared__ float2 aff[8];   // y -> y * aff.x + aff.y  (normalisation and affine folded)
+  const int oc = blockIdx.y, b = blockIdx.z, tid = threadIdx.x;
+  if (tid < 80) ws[tid >> 3][tid & 7] = __ldg(w0 + (tid >> 3) * HB_C + oc * 8 + (tid & 7));
+  if (tid < 8) {
+    const int c = oc * 8 + tid;
+    const float2 st = stats[(size_t)b * HB_C + c];
+    const float g = __ldg(gamma + c) * st.y;
+    aff[tid] = make_float2(g, __ldg(beta + c) - st.x * g);
+  }
+  __syncthreads();
+  const int t = blockIdx.x * 128 + tid;
+  if (t >= T0) return;
+  const float* xb = wav + (size_t)b * N;
+  float x[10];
+#pragma unroll
+  for (int j = 0; j < 10; ++j) {
+    const int i = 5 * t - 40 + j;
+    x[j] = (i >= 0 && i < N) ? __ldg(xb + i) : 0.f;
+  }
+  __align__(16) __nv_bfloat16 hv[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    float y = 0.f;
+#pragma unroll
+    for (int j = 0; j < 10; ++j) y = fmaf(ws[j][e], x[j], y);
+    const float v = fmaf(y, aff[e].x, aff[e].y);
+    hv[e] = __float2bfloat16_rn(0.5f * v * (1.f + erff(v * 0.70710678118654752440f)));
+  }
+  const uint4 pk = *reinterpret_cast<const uint4*>(hv);
+  constexpr int KT = 3 * HB_C / 64;
+  auto put = [&](int t2, int j) {
+    if (t2 >= 0 && t2 < T1) {
+      const int m = b * T1 + t2, k = j * HB_C + oc * 8;
+      *reinterpret_cast<uint4*>(img + ((size_t)(m >> 7) * KT + (k >> 6)) * 8192 + (size_t)((k & 63) >> 3) * 1024 + (size_t)(m & 127) * 8) = pk;
+    }
+  };
+  if (t & 1) put((t - 1) >> 1, 1);
+  else { put(t >> 1, 0); put((t >> 1) - 1, 2); }
+}
+
 static size_t align256h(size_t x) { return (x + 255) & ~(size_t)255; }
 
 struct HLayout {
   int T[7];            // frames after conv0 .. conv6
   int M;
-  size_t bufa, bufb, imgb, posimg, rows, a512, x, y, a, qkv, att, mid, total;   // bufb doubles as the first im2col image
+  size_t bufa, bufb, imgb, stats, posimg, rows, a512, x, y, a, qkv, att, mid, total;   // bufb doubles as the first im2col image
 };
 static HLayout hubert_layout(int B, int n_samples) {
   HLayout L;
@@ -92,6 +177,7 @@ static HLayout hubert_layout(int B, int n_samples) {
     L.bufb = off; off = align256h(off + std::max((size_t)B * HB_C * (L.T[1] > 0 ? L.T[1] : 1) * 4, m1 * 3 * HB_C * 2));
     L.imgb = off; off = align256h(off + m2 * 3 * HB_C * 2);
   }
+  L.stats = off; off = align256h(off + (size_t)B * HB_C * sizeof(float2));
   L.posimg = off; off = align256h(off + Mp * (size_t)HB_PK * (HB_D / HB_PG) * 2);   // one group's im2col image, K = 128 * 48
   L.rows = off; off = align256h(off + (size_t)(L.M > 0 ? L.M : 1) * HB_C * 4);
   L.a512 = off; off = align256h(off + Mp * HB_C * 2);
@@ -210,7 +296,7 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
     if (taps && taps[i]) SVCB_CUDA_CHECK(cudaMemcpyAsync(taps[i], src, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
     return SVCB_OK;
   };
-  {  // conv0 over the zero-padded audio (pad 40 + 40, hubert_model.py:70) -> [B, 512, T0]
+  if (flags & 1) {  // conv0 over the zero-padded audio (pad 40 + 40, hubert_model.py:70) -> [B, 512, T0]
     ConvParams p;
     p.x = wav; p.sxb = n_samples; p.sxc = n_samples; p.sxt = 1;
     p.w = h->conv0_w; p.cout_pad = HB_C; p.bias = nullptr;
@@ -218,7 +304,7 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
     p.B = B; p.Cin = 1; p.Cout = HB_C; p.Tin = n_samples; p.K = 10; p.stride = 5; p.pad = 40; p.nq = L.T[0];
     SVCB_TRY(launch_conv1d(p, s));
   }
-  {
+  if (flags & 1) {
     KernelScope ks("groupnorm_gelu_rows", s, 0.0, 16.0 * B * HB_C * (double)L.T[0]);
     groupnorm_gelu_rows_kernel<<<B * HB_C, 256, 0, s>>>(bufa, h->gn_g, h->gn_b, HB_C, L.T[0], 1e-5f);
     SVCB_LAUNCH_CHECK("groupnorm_gelu_rows");
@@ -226,7 +312,20 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
   if (!(flags & 1)) {
     // conv1 .. conv6 + GELU on the tensor cores: A_i[b * T_i + t][j * 512 + ci] = h_{i-1}[b][ci][2 t + j]
     void* img[2] = {base + L.bufb, base + L.imgb};
-    SVCB_TRY(launch_im2col_s2_image(bufa, img[0], B, HB_C, L.T[0], L.T[1], s, kHbKernels[0], 0));
+    {  // conv0 + GroupNorm + GELU straight into conv1's image (two passes over the audio, see the kernels)
+      float2* stats = reinterpret_cast<float2*>(base + L.stats);
+      {
+        KernelScope ks("hubert_conv0_stats", s, 20.0 * B * HB_C * (double)L.T[0], 4.0 * B * (double)n_samples);
+        hubert_conv0_stats_kernel<<<dim3(HB_C, B), 256, 0, s>>>(wav, h->conv0_w, stats, n_samples, L.T[0], 1e-5f);
+        SVCB_LAUNCH_CHECK("hubert_conv0_stats");
+      }
+      {
+        KernelScope ks("hubert_conv0_pack", s, 20.0 * B * HB_C * (double)L.T[0], 4.0 * B * (double)n_samples + 2.0 * B * 3 * HB_C * (double)L.T[1]);
+        hubert_conv0_pack_kernel<<<dim3((L.T[0] + 127) / 128, HB_C / 8, B), 128, 0, s>>>(
+            wav, h->conv0_w, stats, h->gn_g, h->gn_b, static_cast<__nv_bfloat16*>(img[0]), n_samples, L.T[0], L.T[1]);
+        SVCB_LAUNCH_CHECK("hubert_conv0_pack");
+      }
+    }
     for (int i = 1; i <= 6; ++i) {
       const int K = kHbKernels[i - 1] * HB_C, Mi = B * L.T[i];
       if (i < 6)   // GELU, scattered into conv_{i+1}'s image
