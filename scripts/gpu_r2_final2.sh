@@ -7,5 +7,3 @@ timeout 1200 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/p
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke.log
 SVCB_DUMP_KERNELS=1 timeout 900 python bench.py > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench exit $?"; tail -1 gpurun_out/bench.log | cut -c1-200; tail -2 gpurun_out/bench.err
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref exit $?"; tail -1 gpurun_out/bench_ref.log | cut -c1-200
-BA="--steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-subconfigs"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --print-units base --csv --log-file gpurun_out/r02_launches.csv python bench.py $BA > gpurun_out/ncu_list.log 2>&1; echo "list exit $?"

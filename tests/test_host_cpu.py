@@ -164,3 +164,30 @@ def test_batch_engine_plan_buckets_equal_length_chunks():
         assert sum(len(range((c[2] - c[1]) * hop)[c[3]:c[4]]) for c in mine) == n * hop - 1
     # 4 utterances of 1000 frames -> one batch of 3 and one of 1
     assert sorted(len(b) for b in batches if chunks[b[0]][2] - chunks[b[0]][1] == 1000) == [1, 3]
+
+
+def test_hubert_chunk_plan_and_pack_inventory():
+    """hubert/inference.py:29-48 as data (20 s chunks, the remainder as a last shorter one) and the names / sizes the C side
+    resolves from the packed blob (csrc/hubert_api.cu:svcb_hubert_create) for a 1-layer synthetic checkpoint."""
+    from whisper_vits_svc_b200 import hubert_infer, synth
+    C = hubert_infer.CHUNK
+    assert hubert_infer.chunk_plan(C) == [(0, C)]                       # `while idx + chunk < audln`: an exact chunk is the tail
+    assert hubert_infer.chunk_plan(2 * C + 5) == [(0, C), (C, 2 * C), (2 * C, 2 * C + 5)]
+    assert hubert_infer.chunk_plan(7) == [(0, 7)]
+    sd = synth.hubert_checkpoint(3, n_layer=1)
+    items, n_layer = hubert_infer.pack_hubert(sd)
+    assert n_layer == 1
+    sizes = {n: t.numel() for n, t in items}
+    assert sizes["fe.conv0.w"] == 10 * 512 and sizes["fe.conv1.wimg"] == 512 * 3 * 512 // 2 and sizes["fe.conv6.wimg"] == 512 * 2 * 512 // 2
+    assert sizes["fp.w"] == 768 * 512 // 2 and sizes["proj.w"] == 256 * 768 // 2
+    assert all(sizes[f"pos.{g}.wimg"] == 256 * 128 * 48 // 2 and sizes[f"pos.{g}.bimg"] == 256 for g in range(16))
+    assert all(sizes[f"pos.{g}.{h}.w"] == 48 * 128 * 24 for g in range(16) for h in range(2))
+    assert sizes["L0.wqkv"] == 3 * 768 * 768 // 2 and sizes["L0.w1"] == sizes["L0.w2"] == 3072 * 768 // 2
+    # the grouped positional conv in its tensor-core form: W_g[co][j * 48 + ci] = weight_norm(v, g)[g * 48 + co][ci][j]
+    w = torch._weight_norm(sd["positional_embedding.conv.weight_v"], sd["positional_embedding.conv.weight_g"], 2)
+    img = dict(items)["pos.3.wimg"].view(torch.bfloat16).view(1, 96, 8, 256, 8)     # [N/256][K/64][8 octets][256 rows][8]
+    co, j, ci = 5, 17, 29
+    k = j * 48 + ci
+    got = img[0, k // 64, (k % 64) // 8, co, k % 8].float()
+    assert abs(got - w[3 * 48 + co, ci, j]) <= 4e-3 * abs(w[3 * 48 + co, ci, j]) + 1e-6
+    assert img[0, :, :, 48:, :].abs().max() == 0                                    # padded output channels
