@@ -1,7 +1,8 @@
 // C ABI for the PPG extractor: truncated Whisper AudioEncoder (whisper/model.py:132-163 after the
 // loader's surgery, whisper/inference.py:11-29).  Stage pipeline:
-//   conv1+GELU -> conv2(stride 2)+GELU+pos-emb -> n_layer x { LN -> QKV GEMM -> flash attention ->
-//   out-proj GEMM (+residual) -> LN -> MLP GEMM+GELU -> MLP GEMM (+residual) } -> ln_post
+//   conv1+GELU (GEMM over an im2col image of the log-mel; its epilogue scatters into conv2's im2col image) ->
+//   conv2(stride 2)+GELU+pos-emb (GEMM) -> n_layer x { LN -> QKV GEMM (head-major panels) -> tcgen05 attention
+//   (whisper_attn_tc.cu) -> out-proj GEMM (+residual) -> LN -> MLP GEMM+GELU -> MLP GEMM (+residual) } -> ln_post
 #include <algorithm>
 #include <cstring>
 #include <map>

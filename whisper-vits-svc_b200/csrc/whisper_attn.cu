@@ -5,8 +5,9 @@
 // (= scores * d^-1/2), softmax in fp32, w @ v — without materialising the [B,20,T,T] score tensor.
 // bf16 mma.sync (m16n8k16) tiles, fp32 online softmax; one CTA = 64 queries of one head, 4 warps x
 // 16 rows; K/V tiles of 64 keys double-buffered with cp.async in an XOR-swizzled layout that keeps
-// ldmatrix conflict-free.  (The GEMMs around it carry 84% of the encoder FLOPs and run on tcgen05;
-// attention's 16% stays on the warp-level tensor path this round — DESIGN.md §Whisper.)
+// ldmatrix conflict-free.  Round 1's encoder ran this kernel (247 TFLOP/s); since round 2 the encoder and HuBERT use the
+// tcgen05 kernel of whisper_attn_tc.cu and this one only backs the unit-test entry point `svcb_op_attention_bf16`
+// (an independent implementation the tcgen05 kernel is also compared with).
 #include "common.cuh"
 #include "tc.cuh"
 
