@@ -76,36 +76,49 @@ groupnorm_gelu_rows_kernel(float* __restrict__ x, const float* __restrict__ gamm
 // ---- conv0 + GroupNorm + GELU + the first im2col image in two passes over the AUDIO instead of three over the 2.1 GB
 // conv0 output (conv1d 3.3 + GroupNorm 1.5 + im2col 2.5 ms per 16 x 20 s): conv0 has one input channel and 10 taps, so
 // recomputing it costs less than storing it.
-// pass 1: mean / rstd of every (item, channel) row of y[b, c, t] = sum_j w[c][j] wav[b][5 t + j - 40]
+// pass 1: mean / rstd of every (item, channel) row of y[b, c, t] = sum_j w[c][j] wav[b][5 t + j - 40].  One CTA = (item,
+// octet of channels): a thread loads its 10-sample window once and feeds 8 channels (one channel per CTA was bound by
+// load issue: 10 LDG per FMA chain, 1.8 ms per 16 x 20 s).
 __global__ void __launch_bounds__(256)
 hubert_conv0_stats_kernel(const float* __restrict__ wav, const float* __restrict__ w0, float2* __restrict__ stats, int N,
                           int T0, float eps) {
-  __shared__ double red[2][8];
-  const int c = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double red[16][8];
+  __shared__ float ws[10][8];
+  const int oc = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 80) ws[tid >> 3][tid & 7] = __ldg(w0 + (tid >> 3) * HB_C + oc * 8 + (tid & 7));   // packed [1][10][512]
+  __syncthreads();
   const float* xb = wav + (size_t)b * N;
-  float w[10];
+  double s[8], q[8];
 #pragma unroll
-  for (int j = 0; j < 10; ++j) w[j] = __ldg(w0 + j * HB_C + c);   // packed [1][10][512]
-  double s = 0.0, q = 0.0;
+  for (int e = 0; e < 8; ++e) { s[e] = 0.0; q[e] = 0.0; }
   for (int t = tid; t < T0; t += 256) {
     const int i0 = 5 * t - 40;
-    float y = 0.f;
+    float x[10];
 #pragma unroll
     for (int j = 0; j < 10; ++j) {
       const int i = i0 + j;
-      if (i >= 0 && i < N) y = fmaf(w[j], __ldg(xb + i), y);
+      x[j] = (i >= 0 && i < N) ? __ldg(xb + i) : 0.f;
     }
-    s += y; q += (double)y * y;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float y = 0.f;
+#pragma unroll
+      for (int j = 0; j < 10; ++j) y = fmaf(ws[j][e], x[j], y);
+      s[e] += y; q[e] += (double)y * y;
+    }
   }
 #pragma unroll
-  for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
-  if (lane == 0) { red[0][warp] = s; red[1][warp] = q; }
+  for (int e = 0; e < 8; ++e) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) { s[e] += __shfl_xor_sync(0xffffffffu, s[e], off); q[e] += __shfl_xor_sync(0xffffffffu, q[e], off); }
+    if (lane == 0) { red[e][warp] = s[e]; red[8 + e][warp] = q[e]; }
+  }
   __syncthreads();
-  if (tid == 0) {
+  if (tid < 8) {
     double S = 0.0, Q = 0.0;
-    for (int i = 0; i < 8; ++i) { S += red[0][i]; Q += red[1][i]; }
+    for (int i = 0; i < 8; ++i) { S += red[tid][i]; Q += red[8 + tid][i]; }
     const double mean = S / T0, var = Q / T0 - mean * mean;
-    stats[(size_t)b * HB_C + c] = make_float2((float)mean, (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps)));
+    stats[(size_t)b * HB_C + oc * 8 + tid] = make_float2((float)mean, (float)(1.0 / sqrt((var > 0.0 ? var : 0.0) + (double)eps)));
   }
 }
 
@@ -316,7 +329,7 @@ int svcb_hubert_units(const svcb_hubert* h, const float* wav, float* out, int32_
       float2* stats = reinterpret_cast<float2*>(base + L.stats);
       {
         KernelScope ks("hubert_conv0_stats", s, 20.0 * B * HB_C * (double)L.T[0], 4.0 * B * (double)n_samples);
-        hubert_conv0_stats_kernel<<<dim3(HB_C, B), 256, 0, s>>>(wav, h->conv0_w, stats, n_samples, L.T[0], 1e-5f);
+        hubert_conv0_stats_kernel<<<dim3(HB_C / 8, B), 256, 0, s>>>(wav, h->conv0_w, stats, n_samples, L.T[0], 1e-5f);
         SVCB_LAUNCH_CHECK("hubert_conv0_stats");
       }
       {
