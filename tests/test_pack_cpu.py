@@ -187,3 +187,52 @@ def test_conv_s2d_matrices_are_the_dilated_conv(C, k, dil):
     Y = sum(Xp[:, i:i + n] @ W[i].t() for i in range(mlo + mhi + 1))
     y = Y.view(2, n, C, r).permute(0, 2, 1, 3).reshape(2, C, -1)
     assert (y - ref).abs().max() <= 1e-4
+
+
+@pytest.mark.parametrize("n", [7, 8, 301, 3000])
+def test_conv2_image_scatter_rule(n):
+    """csrc/whisper_gemm.cu epilogue 5: conv1's output frame t lands in conv2's im2col image at (t/2, tap 1) when even and
+    at ((t+1)/2, tap 0), ((t-1)/2, tap 2) when odd — together exactly A2[t2][j] = h1[2 t2 + j - 1] (zero for t = -1 / n)."""
+    n2 = (n - 1) // 2 + 1
+    h1 = np.arange(1, n + 1, dtype=np.float64)
+    want = np.zeros((n2, 3))
+    for t2 in range(n2):
+        for j in range(3):
+            t = 2 * t2 + j - 1
+            if 0 <= t < n:
+                want[t2, j] = h1[t]
+    got = np.zeros((n2, 3))
+    for t in range(n):
+        if t & 1:
+            if (t + 1) // 2 < n2:
+                got[(t + 1) // 2, 0] = h1[t]
+            got[(t - 1) // 2, 2] = h1[t]
+        else:
+            got[t // 2, 1] = h1[t]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n,taps", [(9, 3), (10, 3), (64015, 3), (8, 2), (9, 2), (2000, 2)])
+def test_valid_stride2_image_scatter_rule(n, taps):
+    """csrc/whisper_gemm.cu epilogue 6 / csrc/hubert_api.cu:hubert_conv0_pack_kernel (HuBERT stem, valid stride-2 convs):
+    frame t = 2 t2 + j feeds (t/2, 0) and (t/2 - 1, 2) when even, ((t-1)/2, 1) when odd; every entry of the next conv's
+    image A[t2][j] = h[2 t2 + j], t2 < (n - taps) // 2 + 1, is written exactly once."""
+    tn = (n - taps) // 2 + 1
+    h = np.arange(1, n + 1, dtype=np.float64)
+    want = np.stack([h[j:j + 2 * tn:2][:tn] for j in range(taps)], 1)
+    got = np.zeros((tn, taps))
+    hits = np.zeros((tn, taps), dtype=np.int64)
+
+    def put(t2, j, v):
+        if 0 <= t2 < tn:
+            got[t2, j] = v
+            hits[t2, j] += 1
+
+    for t in range(n):
+        if t & 1:
+            put((t - 1) >> 1, 1, h[t])
+        else:
+            put(t >> 1, 0, h[t])
+            if taps == 3:
+                put((t >> 1) - 1, 2, h[t])
+    assert np.array_equal(got, want) and (hits == 1).all()
